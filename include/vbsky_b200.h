@@ -1,0 +1,145 @@
+/*
+ * vbsky_b200.h -- C ABI of the B200-native VBSKY hot path (libvbsky_b200.so).
+ *
+ * Drop-in boundary for the ELBO's data-parallel path of jthlab/vbsky: Felsenstein pruning
+ * log-likelihood + gradient over (trees x MC samples x site patterns), the BDSKY tree prior
+ * density + gradient, and the height-transform chain between them.  The reference has no FFI
+ * of its own (it is pure Python on JAX); every entry point below cites the reference call it
+ * replaces (file:line under /root/reference/vbsky).  INTEGRATION.md shows the jax.ffi /
+ * ctypes bindings.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / jax types.  "dev" pointers are CUDA device pointers
+ *     in the current device's primary context, "host" pointers are ordinary host memory.
+ *   - every call returns 0 on success or a negative VBSKY_E* code; vbsky_last_error() returns
+ *     the calling thread's last message.  Nothing throws across the ABI.
+ *   - device work is enqueued on the given stream (a cudaStream_t passed as void*) and is
+ *     asynchronous unless the name ends in _host; no global mutable state; handles are
+ *     immutable after creation and may be shared by threads.
+ *   - arrays are row-major; node indices int32; reals are fp64 (dtype "f64").
+ *   - node numbering is the reference's (tree_data.py:464-507): tips 0..n-1, internal nodes
+ *     n..2n-2 with children < parent, root = 2n-2.
+ *   - a "unit" is one (tree, Monte-Carlo sample) pair; unit u uses tree unit_tree[u].
+ */
+#ifndef VBSKY_B200_H
+#define VBSKY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBSKY_OK 0
+#define VBSKY_EINVAL (-1)   /* bad argument / shape / malformed tree */
+#define VBSKY_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define VBSKY_ENOMEM (-3)   /* workspace too small / allocation failure */
+#define VBSKY_EKEY (-4)     /* unknown sequence character (reference: KeyError, substitution.py:48) */
+
+const char* vbsky_last_error(void);
+int vbsky_version(void);
+/* Number of CUDA devices visible; <0 on error.  The product path has no CPU fallback. */
+int vbsky_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Substitution model: mirrors SubstitutionModel(pi, P, d, Pinv) (substitution.py:51-55).
+ * expm(t) = P diag(exp(t d)) Pinv (substitution.py:61-62), Q = P diag(d) Pinv (:57-59).      */
+typedef struct vbsky_subst_model {
+  double pi[4];
+  double P[16];
+  double d[4];
+  double Pinv[16];
+} vbsky_subst_model;
+
+/* HKY(kappa) with uniform base frequencies as substitution.py:73-87 builds it from
+ * msprime.HKY: off-diagonal rates 1/(2+kappa) (transversion), kappa/(2+kappa) (transition),
+ * diagonal -1.  Closed-form spectrum (no LAPACK); the degenerate eigen-pair's basis differs
+ * from eigh's but P f(d) Pinv is identical.  JC69 == HKY(1) (substitution.py:90-92).          */
+int vbsky_hky(double kappa, vbsky_subst_model* out);
+/* Q = P diag(d) Pinv into q[16]. */
+int vbsky_subst_rate_matrix(const vbsky_subst_model* m, double* q);
+
+/* ------------------------------------------------------------------------------------------
+ * Tip encoding and site-pattern compression (host, bit-exact).
+ * Codes are 4-bit state masks: bit0=A bit1=C bit2=G bit3=T, i.e. the {0,1}^4 rows of
+ * PARTIAL_DICT (substitution.py:10-35) packed into one byte.                                 */
+
+/* encode_partials (substitution.py:38-48) for n sequences of length L (seqs[i*L + l]):
+ * writes codes[l*n + i] (site-major, tips in the given order).  Unknown or lower-case
+ * characters give VBSKY_EKEY like the reference's KeyError.                                  */
+int vbsky_encode_tips(const char* seqs, int64_t n, int64_t L, uint8_t* codes);
+
+/* np.unique(tip_partials, axis=0, return_counts=True) of fasta.py:547 on packed codes:
+ * rows of codes[L][n] sorted lexicographically (by the unpacked [n,4] 0/1 rows, which is the
+ * order NumPy gives), duplicates merged.  Optional perm[n] first permutes the columns (tips)
+ * like tip_partials0[:, perm] (fasta.py:545-546).  Outputs patterns[S][n], counts[S]; both
+ * buffers must hold L rows.                                                                  */
+int vbsky_compress_patterns(const uint8_t* codes, int64_t L, int64_t n, const int64_t* perm,
+                            uint8_t* patterns, int64_t* counts, int64_t* S_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Tree layout: an ensemble of T trees with n tips each, given as the reference's TreeData
+ * arrays (tree_data.py:17-23).  Builds, per tree, the evaluation schedules of the pruning
+ * kernel (a depth-first order that keeps all live partial vectors on chip), the level order
+ * of the height transform, siblings (tree_data.py:68-78) and lower sampling times
+ * (tree_data.py:80-117), and uploads them to the current device.
+ * Validates: children < parent for internal nodes, root == 2n-2, child_parent[root] == -1,
+ * parent_child consistent with child_parent.                                                 */
+typedef struct vbsky_layout vbsky_layout;
+
+int vbsky_layout_create(int32_t T, int32_t n,
+                        const int32_t* parent_child /* host [T][2n-1][2] */,
+                        const int32_t* child_parent /* host [T][2n-1]    */,
+                        const int32_t* postorder    /* host [T][2n-1]    */,
+                        const double* sample_times  /* host [T][n]       */,
+                        vbsky_layout** out);
+void vbsky_layout_destroy(vbsky_layout* lay);
+/* info[0]=T, [1]=n, [2]=max live vectors in the up pass, [3]=same for the down pass,
+ * [4]=max number of levels of the height transform. */
+int vbsky_layout_info(const vbsky_layout* lay, int32_t info[8]);
+/* Host copies for inspection / tests: up[n-1][4], down[n-1][4] (encoding in DESIGN.md),
+ * down_nodes[2n-2] (node whose branch gradient each down-pass output slot holds),
+ * lower_sampling_times[2n-1], siblings[2n-1].  Any output may be NULL.                       */
+int vbsky_layout_get(const vbsky_layout* lay, int32_t t, int32_t* up, int32_t* down,
+                     int32_t* down_nodes, double* lower_sampling_times, int32_t* siblings);
+
+/* ------------------------------------------------------------------------------------------
+ * Tip data of the ensemble on the device: TipData(partials[S,n,4], counts[S]) per tree
+ * (util.py:13-15) after pad_tips (fasta.py:325-331), as packed codes.
+ * patterns: host [T][S][n] 4-bit masks (row s of tree t = pattern s over tips in node order);
+ * counts:   host [T][S] pattern multiplicities (0 for padding rows).                          */
+typedef struct vbsky_tips vbsky_tips;
+
+int vbsky_tips_create(int32_t T, int32_t n, int64_t S, const uint8_t* patterns,
+                      const double* counts, vbsky_tips** out);
+void vbsky_tips_destroy(vbsky_tips* tips);
+
+/* ------------------------------------------------------------------------------------------
+ * Pruning likelihood and gradient.  Replaces, for all units at once,
+ *     vmap(prune.prune_loglik, (None,None,0,...))(bl, Q, partials, td) * counts   (bdsky.py:331-343)
+ * and its custom derivative prune_loglik_jvp (prune.py:134-150, eq. 9).
+ *
+ *   unit_tree  host [U]            tree index of each unit
+ *   bl         dev  [U][2n-2]      branch length above each node, ALREADY times clock_rate
+ *   site_ll    dev  [U][S]         per-pattern log-likelihood (prune_loglik's value); may be NULL
+ *   ll         dev  [U]            sum_s counts[s] * site_ll[s]
+ *   dll_dbl    dev  [U][2n-2]      d ll / d bl; NULL => value only (no scratch traffic at all)
+ *   ws         dev                 workspace of >= vbsky_prune_workspace_bytes(...) bytes
+ * Gradients w.r.t. Q, pi and the tip partials are not produced (prune.py:149).                */
+size_t vbsky_prune_workspace_bytes(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                   int32_t want_grad);
+int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                               const int32_t* unit_tree, const double* bl,
+                               const vbsky_subst_model* model, double* site_ll, double* ll,
+                               double* dll_dbl, void* ws, size_t ws_bytes, void* stream);
+
+/* Counters of the last prune call made by this thread: out[0]=kernel launches,
+ * out[1]=persistent CTAs, out[2]=sites per CTA tile, out[3]=dynamic smem bytes per CTA,
+ * out[4]=algorithmic HBM bytes of the fused pruning kernel (DESIGN.md formula).               */
+int vbsky_prune_last_stats(int64_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBSKY_B200_H */

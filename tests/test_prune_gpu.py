@@ -1,0 +1,100 @@
+"""GPU parity: CUDA pruning kernel (through the C ABI) vs the NumPy oracle of prune.py.
+Tolerances are BASELINE.json's: 1e-9 relative on per-site / total log-likelihoods, 1e-6 relative
+on gradients (fp64)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle.prune as oprune
+import oracle.substitution as osub
+import oracle.tree_data as otd
+from oracle.util import TipData
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9
+GRAD_RTOL = 1e-6
+
+
+def _oracle_td(td):
+    return otd.TreeData(td.postorder, td.child_parent, td.parent_child, td.sample_times)
+
+
+def _check(ens_data, kappa, cuda, K):
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, codes_to_partials
+
+    Q = HKY(kappa)
+    oQ = osub.HKY(kappa)
+    ens = Ensemble(ens_data.tds, ens_data.tips, Q, device=cuda)
+    T = len(ens_data.tds)
+    bl = np.stack([ens_data.heights[t].branch_lengths[k] for t in range(T) for k in range(K)]) * ens_data.clock_rate
+    unit_tree = np.repeat(np.arange(T, dtype=np.int32), K)
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), torch.as_tensor(unit_tree, device=cuda),
+                              want_grad=True, want_site_ll=True)
+    ll_v, _, site_v = ens.prune(torch.as_tensor(bl, device=cuda), torch.as_tensor(unit_tree, device=cuda),
+                                want_grad=False, want_site_ll=True)
+    torch.cuda.synchronize()
+    ll, dll, site = ll.cpu().numpy(), dll.cpu().numpy(), site.cpu().numpy()
+    assert np.array_equal(ll, ll_v.cpu().numpy())
+    assert np.array_equal(site, site_v.cpu().numpy())
+    for u in range(T * K):
+        t = unit_tree[u]
+        td = _oracle_td(ens_data.tds[t])
+        part = codes_to_partials(ens_data.tips[t].patterns)
+        tot, g, sll = oprune.data_loglik_and_grad(bl[u], oQ, part, ens_data.tips[t].counts, td)
+        np.testing.assert_allclose(site[u], sll, rtol=LL_RTOL, atol=0)
+        np.testing.assert_allclose(ll[u], tot, rtol=LL_RTOL, atol=0)
+        np.testing.assert_allclose(dll[u], g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    ens.close()
+
+
+@pytest.mark.parametrize("T,n,S,K,kappa,clock", [
+    (2, 2, 50, 2, 2.7, 0.05),
+    (3, 3, 129, 2, 1.0, 0.1),
+    (2, 10, 300, 3, 2.7, 0.05),
+    (2, 63, 411, 2, 2.7, 1.12e-3),
+    (1, 200, 1000, 2, 2.7, 1.12e-3),
+    (1, 500, 700, 1, 2.7, 1.0),
+])
+def test_prune_matches_oracle(cuda, T, n, S, K, kappa, clock):
+    from vbsky_b200.substitution import HKY
+    from vbsky_b200.synth import make_ensemble
+
+    data = make_ensemble(T, n, S, K, seed=n * 1000 + S, Q=HKY(kappa), clock_rate=clock, missing=0.05)
+    _check(data, kappa, cuda, K)
+
+
+def test_prune_compressed_patterns_and_padding(cuda):
+    from vbsky_b200.substitution import HKY
+    from vbsky_b200.synth import make_ensemble
+
+    data = make_ensemble(3, 12, 2000, 2, seed=7, Q=HKY(2.7), clock_rate=0.02, compress=True)
+    assert any((t.counts == 0).any() for t in data.tips) or len({t.patterns.shape[0] for t in data.tips}) == 1
+    _check(data, 2.7, cuda, 2)
+
+
+def test_prune_caterpillar_and_ambiguity(cuda):
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, codes_to_partials, encode_codes
+    from vbsky_b200.synth import random_tree, sample_heights
+    from vbsky_b200.tips import PackedTips
+
+    rng = np.random.default_rng(3)
+    n, L = 40, 333
+    td = random_tree(n, rng, caterpillar=True)
+    sh = sample_heights(td, 2, rng, origin=2.0)
+    seqs = ["".join(rng.choice(list("ACGTUNX-?RYMWSKBDHV"), L)) for _ in range(n)]
+    codes = encode_codes(seqs)
+    tips = PackedTips(codes, rng.integers(0, 5, L).astype(np.float64))
+    Q, oQ = HKY(2.7), osub.HKY(2.7)
+    ens = Ensemble([td], [tips], Q, device=cuda)
+    bl = sh.branch_lengths * 0.3
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), torch.zeros(2, dtype=torch.int32, device=cuda),
+                              want_grad=True, want_site_ll=True)
+    for u in range(2):
+        tot, g, sll = oprune.data_loglik_and_grad(bl[u], oQ, codes_to_partials(codes), tips.counts, _oracle_td(td))
+        np.testing.assert_allclose(site[u].cpu().numpy(), sll, rtol=LL_RTOL)
+        np.testing.assert_allclose(ll[u].item(), tot, rtol=LL_RTOL)
+        np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    ens.close()

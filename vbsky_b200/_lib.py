@@ -1,0 +1,86 @@
+"""ctypes binding of libvbsky_b200.so (the C ABI declared in include/vbsky_b200.h).
+
+The shared library is built in-tree by ``vbsky_b200/csrc/Makefile`` (see ``__graft_entry__.build``).
+There is no CPU fallback: if the library is missing, importing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvbsky_b200.so")
+
+
+class VbskyError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[vbsky_b200 {code}] {msg}")
+        self.code = code
+
+
+class VbskyKeyError(VbskyError, KeyError):
+    """Unknown sequence character (the reference raises KeyError, substitution.py:48)."""
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `make -C vbsky_b200/csrc` "
+        "(or `python -c 'import __graft_entry__ as g; g.build()'`). vbsky_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+
+class SubstModel(C.Structure):
+    _fields_ = [("pi", C.c_double * 4), ("P", C.c_double * 16), ("d", C.c_double * 4), ("Pinv", C.c_double * 16)]
+
+
+_vp = C.c_void_p
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+
+# name -> (restype, argtypes); every symbol of include/vbsky_b200.h must appear here
+# (tests/test_cabi.py checks the header against this table and against the .so).
+SIGNATURES = {
+    "vbsky_last_error": (C.c_char_p, []),
+    "vbsky_version": (C.c_int, []),
+    "vbsky_device_count": (C.c_int, []),
+    "vbsky_hky": (C.c_int, [C.c_double, C.POINTER(SubstModel)]),
+    "vbsky_subst_rate_matrix": (C.c_int, [C.POINTER(SubstModel), _f64p]),
+    "vbsky_encode_tips": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _u8p]),
+    "vbsky_compress_patterns": (C.c_int, [_u8p, C.c_int64, C.c_int64, _i64p, _u8p, _i64p, _i64p]),
+    "vbsky_layout_create": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, C.POINTER(_vp)]),
+    "vbsky_layout_destroy": (None, [_vp]),
+    "vbsky_layout_info": (C.c_int, [_vp, _i32p]),
+    "vbsky_layout_get": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _f64p, _i32p]),
+    "vbsky_tips_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _u8p, _f64p, C.POINTER(_vp)]),
+    "vbsky_tips_destroy": (None, [_vp]),
+    "vbsky_prune_workspace_bytes": (C.c_size_t, [_vp, _vp, C.c_int32, C.c_int32]),
+    "vbsky_prune_value_and_grad": (
+        C.c_int,
+        [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _vp, _vp, _vp, _vp, C.c_size_t, _vp],
+    ),
+    "vbsky_prune_last_stats": (C.c_int, [_i64p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return lib.vbsky_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        msg = last_error()
+        if rc == -4:
+            raise VbskyKeyError(rc, msg)
+        raise VbskyError(rc, msg)
+    return rc
+
+
+def np_ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))

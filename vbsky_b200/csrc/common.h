@@ -1,0 +1,74 @@
+// Shared host-side helpers of libvbsky_b200: error reporting and handle definitions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "vbsky_b200.h"
+
+namespace vbsky {
+
+int set_error(int code, const char* fmt, ...);
+
+#define VB_CHECK_ARG(cond, ...)                                      \
+  do {                                                               \
+    if (!(cond)) return ::vbsky::set_error(VBSKY_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define VB_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ::vbsky::set_error(VBSKY_ECUDA, "%s failed: %s (%s:%d)", #expr,           \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);            \
+  } while (0)
+
+// One step of the up (postorder) pass: combine children a and b into parent p.
+//   x = a, y = b, z = p, w = slotA | slotB<<8 | slotOut<<16   (on-chip slots of internal children / result)
+// One step of the down (preorder) pass: expand parent p into children a and b.
+//   x = a | b<<16, y = scrA | scrB<<16 (scratch rows holding the children's messages; 0xffff for tips),
+//   z = slotP | slotA<<8 | slotB<<16, w = p
+struct Op {
+  int32_t x, y, z, w;
+};
+
+}  // namespace vbsky
+
+struct vbsky_layout {
+  int32_t T = 0, n = 0, N = 0;
+  int32_t depth_up = 0, depth_down = 0, max_levels = 0;
+  // host copies
+  std::vector<vbsky::Op> h_up, h_down;        // [T][n-1]
+  std::vector<int32_t> h_down_nodes;          // [T][2n-2]
+  std::vector<int32_t> h_child_parent;        // [T][N]
+  std::vector<int32_t> h_siblings;            // [T][N]
+  std::vector<double> h_lst;                  // [T][N]
+  std::vector<double> h_sample_times;         // [T][n]
+  std::vector<double> h_max_sample_time;      // [T]
+  std::vector<int32_t> h_level_nodes;         // [T][n-1] internal nodes ordered by depth (root first)
+  std::vector<int32_t> h_level_start;         // [T][max_levels+1]
+  // device copies
+  vbsky::Op* d_up = nullptr;
+  vbsky::Op* d_down = nullptr;
+  int32_t* d_down_nodes = nullptr;
+  int32_t* d_child_parent = nullptr;
+  double* d_lst = nullptr;
+  double* d_sample_times = nullptr;
+  double* d_max_sample_time = nullptr;
+  int32_t* d_level_nodes = nullptr;
+  int32_t* d_level_start = nullptr;
+  int device = -1;
+};
+
+struct vbsky_tips {
+  int32_t T = 0, n = 0;
+  int64_t S = 0;        // patterns per tree as given
+  int64_t S_pad = 0;    // padded to the kernel's tile multiple
+  uint8_t* d_codes = nullptr;  // [T][n][S_pad] code ranks (see tips.cu), tip-major / site-minor
+  double* d_counts = nullptr;  // [T][S_pad], 0 on padding
+  int device = -1;
+};

@@ -1,0 +1,333 @@
+// Tree layout: validation of the reference's TreeData arrays and construction of the pruning
+// kernel's evaluation schedules (host), plus upload.  See include/vbsky_b200.h and DESIGN.md.
+//
+// The reference walks parents in index order n..2n-2 (prune.py:49) and children in reversed
+// postorder (prune.py:95), materialising every partial vector.  Per-node results do not depend
+// on the visiting order, so the schedules here are chosen to keep the number of simultaneously
+// live vectors minimal (a Strahler / Sethi-Ullman ordering, <= log2(n)+1 for any binary tree),
+// which lets the kernel hold them in shared memory.
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+
+namespace vbsky {
+
+static thread_local std::string g_err;
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+namespace {
+
+struct SlotPool {
+  std::vector<char> used;
+  int high = 0;
+  int alloc() {
+    for (size_t i = 0; i < used.size(); ++i)
+      if (!used[i]) {
+        used[i] = 1;
+        high = std::max(high, (int)i + 1);
+        return (int)i;
+      }
+    used.push_back(1);
+    high = std::max(high, (int)used.size());
+    return (int)used.size() - 1;
+  }
+  void release(int s) { used[s] = 0; }
+};
+
+// Build both schedules of one tree.  pc = parent_child [N][2].
+int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, int* depth_up,
+               int* depth_down) {
+  const int N = 2 * n - 1, root = N - 1;
+  auto internal = [n](int v) { return v >= n; };
+
+  // ---- up pass: need[v] = peak number of live message slots while evaluating subtree v.
+  std::vector<int> need(N, 0), first(N, 0);  // first[v]: which child (0/1) is evaluated first
+  for (int v = n; v < N; ++v) {
+    const int c[2] = {pc[2 * v], pc[2 * v + 1]};
+    int best = 1 << 30, bestf = 0;
+    for (int f = 0; f < 2; ++f) {
+      const int a = c[f], b = c[1 - f];
+      const int ha = internal(a), hb = internal(b);
+      const int peak = std::max({need[a], ha + need[b], std::max(ha + hb, 1)});
+      if (peak < best) best = peak, bestf = f;
+    }
+    need[v] = best;
+    first[v] = bestf;
+  }
+  // emit in DFS order (explicit stack: (node, state))
+  std::vector<int> up_row(N, -1), slot_of(N, -1);
+  {
+    std::vector<std::pair<int, int>> st;
+    st.push_back({root, 0});
+    SlotPool pool;
+    int step = 0;
+    while (!st.empty()) {
+      auto& top = st.back();
+      const int v = top.first;
+      const int a = pc[2 * v + first[v]], b = pc[2 * v + 1 - first[v]];
+      if (top.second == 0) {
+        top.second = 1;
+        if (internal(a)) {
+          st.push_back({a, 0});
+          continue;
+        }
+      }
+      if (st.back().second == 1) {
+        st.back().second = 2;
+        if (internal(b)) {
+          st.push_back({b, 0});
+          continue;
+        }
+      }
+      // both children done: emit v
+      int sa = 0xff, sb = 0xff, so = 0xff;
+      if (internal(a)) sa = slot_of[a], pool.release(sa);
+      if (internal(b)) sb = slot_of[b], pool.release(sb);
+      if (v != root) so = pool.alloc(), slot_of[v] = so;
+      if (so != 0xff && so >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
+      up[step] = Op{a, b, v, sa | (sb << 8) | (so << 16)};
+      up_row[v] = step;
+      ++step;
+      st.pop_back();
+    }
+    if (step != n - 1) return set_error(VBSKY_EINVAL, "internal error: up schedule has %d steps, expected %d", step, n - 1);
+    *depth_up = std::max(pool.high, 1);
+  }
+
+  // ---- down pass: needd[v] = peak live pre-vectors while expanding subtree v (pre_v held on entry).
+  std::vector<int> needd(N, 0), firstd(N, 0);
+  for (int v = n; v < N; ++v) {
+    const int a = pc[2 * v], b = pc[2 * v + 1];
+    const int ia = internal(a), ib = internal(b);
+    if (!ia && !ib)
+      needd[v] = 1;
+    else if (ia && !ib)
+      needd[v] = std::max(1, needd[a]), firstd[v] = 0;
+    else if (!ia && ib)
+      needd[v] = std::max(1, needd[b]), firstd[v] = 1;
+    else {
+      // descend first into the child with the smaller need while the other's pre vector waits
+      const int f = needd[a] <= needd[b] ? 0 : 1;
+      const int cf = pc[2 * v + f], cs = pc[2 * v + 1 - f];
+      needd[v] = std::max({2, needd[cf] + 1, needd[cs]});
+      firstd[v] = f;
+    }
+  }
+  {
+    std::vector<int> st;
+    st.push_back(root);
+    SlotPool pool;
+    std::fill(slot_of.begin(), slot_of.end(), -1);
+    int step = 0;
+    while (!st.empty()) {
+      const int v = st.back();
+      st.pop_back();
+      const int a = pc[2 * v + firstd[v]], b = pc[2 * v + 1 - firstd[v]];
+      int sp = 0xff, sa = 0xff, sb = 0xff;
+      if (v != root) sp = slot_of[v], pool.release(sp);
+      if (internal(a)) sa = pool.alloc(), slot_of[a] = sa;
+      if (internal(b)) sb = pool.alloc(), slot_of[b] = sb;
+      if ((sa != 0xff && sa >= 0xff) || (sb != 0xff && sb >= 0xff))
+        return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
+      const int ra = internal(a) ? up_row[a] : 0xffff, rb = internal(b) ? up_row[b] : 0xffff;
+      down[step] = Op{a | (b << 16), ra | (rb << 16), sp | (sa << 8) | (sb << 16), v};
+      down_nodes[2 * step] = a;
+      down_nodes[2 * step + 1] = b;
+      ++step;
+      if (internal(b)) st.push_back(b);
+      if (internal(a)) st.push_back(a);  // a is expanded next
+    }
+    if (step != n - 1) return set_error(VBSKY_EINVAL, "internal error: down schedule has %d steps", step);
+    *depth_down = std::max(pool.high, 1);
+  }
+  return VBSKY_OK;
+}
+
+template <class T>
+int upload(T** dptr, const std::vector<T>& h) {
+  VB_CUDA(cudaMalloc((void**)dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) VB_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return VBSKY_OK;
+}
+
+}  // namespace
+}  // namespace vbsky
+
+using namespace vbsky;
+
+extern "C" const char* vbsky_last_error(void) { return g_err.c_str(); }
+extern "C" int vbsky_version(void) { return 100; }
+extern "C" int vbsky_device_count(void) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) return set_error(VBSKY_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return c;
+}
+
+extern "C" void vbsky_layout_destroy(vbsky_layout* lay) {
+  if (!lay) return;
+  cudaFree(lay->d_up);
+  cudaFree(lay->d_down);
+  cudaFree(lay->d_down_nodes);
+  cudaFree(lay->d_child_parent);
+  cudaFree(lay->d_lst);
+  cudaFree(lay->d_sample_times);
+  cudaFree(lay->d_max_sample_time);
+  cudaFree(lay->d_level_nodes);
+  cudaFree(lay->d_level_start);
+  delete lay;
+}
+
+extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_child,
+                                   const int32_t* child_parent, const int32_t* postorder,
+                                   const double* sample_times, vbsky_layout** out) {
+  VB_CHECK_ARG(out != nullptr, "out is NULL");
+  *out = nullptr;
+  VB_CHECK_ARG(T >= 1, "T must be >= 1 (got %d)", T);
+  VB_CHECK_ARG(n >= 2 && n <= 32767, "n must be in [2, 32767] (got %d)", n);
+  VB_CHECK_ARG(parent_child && child_parent && postorder && sample_times, "NULL input array");
+  const int N = 2 * n - 1, root = N - 1;
+
+  auto* lay = new vbsky_layout();
+  lay->T = T, lay->n = n, lay->N = N;
+  lay->h_up.resize((size_t)T * (n - 1));
+  lay->h_down.resize((size_t)T * (n - 1));
+  lay->h_down_nodes.resize((size_t)T * (2 * n - 2));
+  lay->h_child_parent.assign(child_parent, child_parent + (size_t)T * N);
+  lay->h_siblings.assign((size_t)T * N, -1);
+  lay->h_lst.assign((size_t)T * N, 0.0);
+  lay->h_sample_times.assign(sample_times, sample_times + (size_t)T * n);
+  lay->h_max_sample_time.resize(T);
+  lay->h_level_nodes.resize((size_t)T * (n - 1));
+  std::vector<std::vector<int32_t>> level_starts(T);
+
+  int rc = VBSKY_OK;
+  for (int t = 0; t < T && rc == VBSKY_OK; ++t) {
+    const int32_t* pc = parent_child + (size_t)t * N * 2;
+    const int32_t* cp = child_parent + (size_t)t * N;
+    const int32_t* po = postorder + (size_t)t * N;
+    // validation (the reference relies on these silently: prune.py:49, bdsky.py:307)
+    std::vector<char> seen(N, 0);
+    for (int i = 0; i < N && rc == VBSKY_OK; ++i) {
+      if (po[i] < 0 || po[i] >= N || seen[po[i]]) rc = set_error(VBSKY_EINVAL, "tree %d: postorder is not a permutation of 0..%d", t, N - 1);
+      else seen[po[i]] = 1;
+    }
+    if (rc == VBSKY_OK && po[N - 1] != root) rc = set_error(VBSKY_EINVAL, "tree %d: postorder must end at the root %d", t, root);
+    if (rc == VBSKY_OK && cp[root] != -1) rc = set_error(VBSKY_EINVAL, "tree %d: child_parent[root] must be -1", t);
+    for (int v = 0; v < N && rc == VBSKY_OK; ++v) {
+      const int a = pc[2 * v], b = pc[2 * v + 1];
+      if (v < n) {
+        if (a != -1 || b != -1) rc = set_error(VBSKY_EINVAL, "tree %d: leaf %d has children", t, v);
+      } else {
+        if (a < 0 || b < 0 || a >= v || b >= v || a == b) rc = set_error(VBSKY_EINVAL, "tree %d: node %d needs two distinct children with smaller index (got %d, %d)", t, v, a, b);
+        else if (cp[a] != v || cp[b] != v) rc = set_error(VBSKY_EINVAL, "tree %d: parent_child and child_parent disagree at node %d", t, v);
+      }
+      if (rc == VBSKY_OK && v != root && (cp[v] < n || cp[v] >= N)) rc = set_error(VBSKY_EINVAL, "tree %d: node %d has invalid parent %d", t, v, cp[v]);
+    }
+    if (rc != VBSKY_OK) break;
+
+    int du = 0, dd = 0;
+    rc = build_tree(n, pc, &lay->h_up[(size_t)t * (n - 1)], &lay->h_down[(size_t)t * (n - 1)],
+                    &lay->h_down_nodes[(size_t)t * (2 * n - 2)], &du, &dd);
+    if (rc != VBSKY_OK) break;
+    lay->depth_up = std::max(lay->depth_up, du);
+    lay->depth_down = std::max(lay->depth_down, dd);
+
+    // siblings (tree_data.py:68-78) and lower sampling times (tree_data.py:80-117)
+    int32_t* sib = &lay->h_siblings[(size_t)t * N];
+    double* lst = &lay->h_lst[(size_t)t * N];
+    const double* stimes = sample_times + (size_t)t * n;
+    double mx = stimes[0];
+    for (int i = 0; i < n; ++i) lst[i] = stimes[i], mx = std::max(mx, stimes[i]);
+    lay->h_max_sample_time[t] = mx;
+    for (int v = n; v < N; ++v) {
+      const int a = pc[2 * v], b = pc[2 * v + 1];
+      sib[a] = b, sib[b] = a;
+      lst[v] = std::max(lst[a], lst[b]);
+    }
+    // levels of the internal nodes (root = level 0), parents before children
+    std::vector<int> depth(N, 0);
+    int maxd = 0;
+    for (int v = root - 1; v >= n; --v) depth[v] = depth[cp[v]] + 1, maxd = std::max(maxd, depth[v]);
+    std::vector<int32_t>& ls = level_starts[t];
+    ls.assign(maxd + 2, 0);
+    for (int v = n; v < N; ++v) ls[depth[v] + 1]++;
+    for (int l = 0; l <= maxd; ++l) ls[l + 1] += ls[l];
+    std::vector<int> fill(ls.begin(), ls.end() - 1);
+    int32_t* ln = &lay->h_level_nodes[(size_t)t * (n - 1)];
+    for (int v = n; v < N; ++v) ln[fill[depth[v]]++] = v;
+    lay->max_levels = std::max(lay->max_levels, maxd + 1);
+  }
+  if (rc != VBSKY_OK) {
+    delete lay;
+    return rc;
+  }
+  lay->h_level_start.assign((size_t)T * (lay->max_levels + 1), 0);
+  for (int t = 0; t < T; ++t) {
+    int32_t* dst = &lay->h_level_start[(size_t)t * (lay->max_levels + 1)];
+    const auto& ls = level_starts[t];
+    for (int l = 0; l <= lay->max_levels; ++l) dst[l] = l < (int)ls.size() ? ls[l] : ls.back();
+  }
+
+  // Without a visible CUDA device the layout stays host-only (schedules can still be inspected
+  // through vbsky_layout_get); every compute entry point then refuses it -- there is no CPU path.
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    lay->device = -1;
+    *out = lay;
+    return VBSKY_OK;
+  }
+  cudaError_t e = cudaGetDevice(&lay->device);
+  if (e != cudaSuccess) {
+    delete lay;
+    return set_error(VBSKY_ECUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e));
+  }
+#define VB_UP(dst, src)                                 \
+  if ((rc = upload(&lay->dst, lay->src)) != VBSKY_OK) { \
+    vbsky_layout_destroy(lay);                          \
+    return rc;                                          \
+  }
+  VB_UP(d_up, h_up)
+  VB_UP(d_down, h_down)
+  VB_UP(d_down_nodes, h_down_nodes)
+  VB_UP(d_child_parent, h_child_parent)
+  VB_UP(d_lst, h_lst)
+  VB_UP(d_sample_times, h_sample_times)
+  VB_UP(d_max_sample_time, h_max_sample_time)
+  VB_UP(d_level_nodes, h_level_nodes)
+  VB_UP(d_level_start, h_level_start)
+#undef VB_UP
+  *out = lay;
+  return VBSKY_OK;
+}
+
+extern "C" int vbsky_layout_info(const vbsky_layout* lay, int32_t info[8]) {
+  VB_CHECK_ARG(lay && info, "NULL argument");
+  std::memset(info, 0, 8 * sizeof(int32_t));
+  info[0] = lay->T, info[1] = lay->n, info[2] = lay->depth_up, info[3] = lay->depth_down, info[4] = lay->max_levels;
+  return VBSKY_OK;
+}
+
+extern "C" int vbsky_layout_get(const vbsky_layout* lay, int32_t t, int32_t* up, int32_t* down,
+                                int32_t* down_nodes, double* lst, int32_t* siblings) {
+  VB_CHECK_ARG(lay, "NULL layout");
+  VB_CHECK_ARG(t >= 0 && t < lay->T, "tree index %d out of range", t);
+  const int n = lay->n, N = lay->N;
+  if (up) std::memcpy(up, &lay->h_up[(size_t)t * (n - 1)], sizeof(Op) * (n - 1));
+  if (down) std::memcpy(down, &lay->h_down[(size_t)t * (n - 1)], sizeof(Op) * (n - 1));
+  if (down_nodes) std::memcpy(down_nodes, &lay->h_down_nodes[(size_t)t * (2 * n - 2)], sizeof(int32_t) * (2 * n - 2));
+  if (lst) std::memcpy(lst, &lay->h_lst[(size_t)t * N], sizeof(double) * N);
+  if (siblings) std::memcpy(siblings, &lay->h_siblings[(size_t)t * N], sizeof(int32_t) * N);
+  return VBSKY_OK;
+}

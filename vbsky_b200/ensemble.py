@@ -1,0 +1,125 @@
+"""Device-resident ensemble of trees + tip data and the batched calls into the CUDA path.
+
+An ``Ensemble`` is what ``SeqData.prep_data`` (fasta.py:333-360) leaves behind in the reference --
+``tds`` and padded ``tip_data_cs`` -- uploaded once; ``prune`` then evaluates
+``vmap(prune_loglik) * counts`` (bdsky.py:331-343) and its gradient for any batch of
+(tree, sample) units in one call.  PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .substitution import SubstitutionModel
+from .tips import PackedTips
+from .tree_data import TreeData
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Ensemble:
+    def __init__(self, tds: Sequence[TreeData], tips: Sequence[PackedTips], Q: SubstitutionModel,
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vbsky_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.T = len(tds)
+        if self.T < 1 or len(tips) != self.T:
+            raise ValueError("need one tip-data entry per tree")
+        self.n = int(tds[0].n)
+        self.N = 2 * self.n - 1
+        if any(td.n != self.n for td in tds):
+            raise ValueError("all trees of an ensemble must have the same number of tips")
+        self.S = int(tips[0].patterns.shape[0])
+        if any(t.patterns.shape != (self.S, self.n) for t in tips):
+            raise ValueError("tip patterns must be [S, n] with one S for the whole ensemble (use pad_tips)")
+        self.Q = Q
+        self._model = Q.c_struct()
+        self.tds = list(tds)
+
+        pc = np.ascontiguousarray(np.stack([td.parent_child for td in tds]), dtype=np.int32)
+        cp = np.ascontiguousarray(np.stack([td.child_parent for td in tds]), dtype=np.int32)
+        po = np.ascontiguousarray(np.stack([td.postorder for td in tds]), dtype=np.int32)
+        st = np.ascontiguousarray(np.stack([td.sample_times for td in tds]), dtype=np.float64)
+        patterns = np.ascontiguousarray(np.stack([t.patterns for t in tips]), dtype=np.uint8)
+        counts = np.ascontiguousarray(np.stack([t.counts for t in tips]), dtype=np.float64)
+        self._layout = C.c_void_p()
+        self._tips = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.vbsky_layout_create(
+                self.T, self.n, _lib.np_ptr(pc, C.c_int32), _lib.np_ptr(cp, C.c_int32),
+                _lib.np_ptr(po, C.c_int32), _lib.np_ptr(st, C.c_double), C.byref(self._layout)))
+            _lib.check(_lib.lib.vbsky_tips_create(
+                self.T, self.n, self.S, _lib.np_ptr(patterns, C.c_uint8), _lib.np_ptr(counts, C.c_double),
+                C.byref(self._tips)))
+        self._ws = None
+        info = (C.c_int32 * 8)()
+        _lib.check(_lib.lib.vbsky_layout_info(self._layout, info))
+        self.depth_up, self.depth_down, self.max_levels = info[2], info[3], info[4]
+
+    def close(self):
+        if getattr(self, "_layout", None):
+            _lib.lib.vbsky_layout_destroy(self._layout)
+            self._layout = None
+        if getattr(self, "_tips", None):
+            _lib.lib.vbsky_tips_destroy(self._tips)
+            self._tips = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def schedule(self, t: int):
+        """Host copies of tree t's kernel schedules (tests / inspection)."""
+        n = self.n
+        up = np.zeros((n - 1, 4), dtype=np.int32)
+        down = np.zeros((n - 1, 4), dtype=np.int32)
+        dn = np.zeros(2 * n - 2, dtype=np.int32)
+        lst = np.zeros(2 * n - 1)
+        sib = np.zeros(2 * n - 1, dtype=np.int32)
+        _lib.check(_lib.lib.vbsky_layout_get(self._layout, t, _lib.np_ptr(up, C.c_int32), _lib.np_ptr(down, C.c_int32),
+                                              _lib.np_ptr(dn, C.c_int32), _lib.np_ptr(lst, C.c_double),
+                                              _lib.np_ptr(sib, C.c_int32)))
+        return dict(up=up, down=down, down_nodes=dn, lower_sampling_times=lst, siblings=sib)
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def prune(self, bl: torch.Tensor, unit_tree: torch.Tensor, want_grad: bool = True, want_site_ll: bool = False):
+        """bl [U, 2n-2] fp64 (already multiplied by the clock rate), unit_tree [U] int32, both on the
+        device.  Returns (ll [U], dll_dbl [U, 2n-2] or None, site_ll [U, S] or None)."""
+        U = bl.shape[0]
+        if bl.dtype != torch.float64 or bl.device != self.device or bl.shape != (U, 2 * self.n - 2):
+            raise ValueError(f"bl must be a float64 [{U}, {2 * self.n - 2}] tensor on {self.device}")
+        if unit_tree.dtype != torch.int32 or unit_tree.device != self.device or unit_tree.shape != (U,):
+            raise ValueError("unit_tree must be an int32 [U] tensor on the ensemble's device")
+        bl = bl.contiguous()
+        with torch.cuda.device(self.device):
+            need = _lib.lib.vbsky_prune_workspace_bytes(self._layout, self._tips, U, int(want_grad))
+            if need == 0:
+                raise _lib.VbskyError(-1, _lib.last_error())
+            ws = self._workspace(need)
+            ll = torch.empty(U, dtype=torch.float64, device=self.device)
+            dll = torch.empty(U, 2 * self.n - 2, dtype=torch.float64, device=self.device) if want_grad else None
+            site = torch.empty(U, self.S, dtype=torch.float64, device=self.device) if want_site_ll else None
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib.vbsky_prune_value_and_grad(
+                self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model),
+                _ptr(site), _ptr(ll), _ptr(dll), _ptr(ws), ws.numel(), C.c_void_p(stream)))
+        return ll, dll, site
+
+    @staticmethod
+    def last_stats():
+        out = (C.c_int64 * 8)()
+        _lib.check(_lib.lib.vbsky_prune_last_stats(out))
+        return dict(launches=out[0], ctas=out[1], tile=out[2], smem=out[3], algorithmic_bytes=out[4])
