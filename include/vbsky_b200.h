@@ -108,10 +108,12 @@ int vbsky_layout_get(const vbsky_layout* lay, int32_t t, int32_t* up, int32_t* d
  * Tip data of the ensemble on the device: TipData(partials[S,n,4], counts[S]) per tree
  * (util.py:13-15) after pad_tips (fasta.py:325-331), as packed codes.
  * patterns: host [T][S][n] 4-bit masks (row s of tree t = pattern s over tips in node order);
- * counts:   host [T][S] pattern multiplicities (0 for padding rows).                          */
+ * counts:   host [T][S] pattern multiplicities (0 for padding rows).
+ * The codes are stored in the order the layout's schedules consume them, so tips belong to the
+ * layout they were created with (T and n are taken from it).                                  */
 typedef struct vbsky_tips vbsky_tips;
 
-int vbsky_tips_create(int32_t T, int32_t n, int64_t S, const uint8_t* patterns,
+int vbsky_tips_create(const vbsky_layout* lay, int64_t S, const uint8_t* patterns,
                       const double* counts, vbsky_tips** out);
 void vbsky_tips_destroy(vbsky_tips* tips);
 

@@ -53,7 +53,7 @@ SIGNATURES = {
     "vbsky_layout_destroy": (None, [_vp]),
     "vbsky_layout_info": (C.c_int, [_vp, _i32p]),
     "vbsky_layout_get": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _f64p, _i32p]),
-    "vbsky_tips_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _u8p, _f64p, C.POINTER(_vp)]),
+    "vbsky_tips_create": (C.c_int, [_vp, C.c_int64, _u8p, _f64p, C.POINTER(_vp)]),
     "vbsky_tips_destroy": (None, [_vp]),
     "vbsky_prune_workspace_bytes": (C.c_size_t, [_vp, _vp, C.c_int32, C.c_int32]),
     "vbsky_prune_value_and_grad": (

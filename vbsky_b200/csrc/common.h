@@ -28,13 +28,19 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 // One step of the up (postorder) pass: combine children a and b into parent p.
-//   x = a, y = b, z = p, w = slotA | slotB<<8 | slotOut<<16   (on-chip slots of internal children / result)
+//   x = a | b<<16, y = p, z = slotA | slotB<<8 | slotOut<<16 (on-chip stack slots of internal
+//   children / of the result; 0xff = none), w = flags: bit0 a is a tip, bit1 b is a tip, bit2 p is the root.
+//   The message produced by step s is streamed to scratch row s.
 // One step of the down (preorder) pass: expand parent p into children a and b.
-//   x = a | b<<16, y = scrA | scrB<<16 (scratch rows holding the children's messages; 0xffff for tips),
-//   z = slotP | slotA<<8 | slotB<<16, w = p
+//   x = a | b<<16, y = p, z = slotP | slotA<<8 | slotB<<16 (slotP 0xff = root: pre = pi), w = flags as above.
+//   Internal children's messages arrive through the message ring in the order a, b (h_msg_rows).
 struct Op {
   int32_t x, y, z, w;
 };
+
+// Geometry shared by the host-side layout builder and the pruning kernel.
+constexpr int kTile = 128;        // site patterns per CTA tile (= consumer threads per CTA)
+constexpr int kChunkSteps = 4;    // schedule steps delivered per ring stage
 
 }  // namespace vbsky
 
@@ -44,6 +50,8 @@ struct vbsky_layout {
   // host copies
   std::vector<vbsky::Op> h_up, h_down;        // [T][n-1]
   std::vector<int32_t> h_down_nodes;          // [T][2n-2]
+  std::vector<int32_t> h_msg_rows;            // [T][n-2] scratch rows of internal children in down-pass consumption order
+  std::vector<int32_t> h_msg_start;           // [T][nchunks+1] prefix of h_msg_rows per chunk of kChunkSteps down steps
   std::vector<int32_t> h_child_parent;        // [T][N]
   std::vector<int32_t> h_siblings;            // [T][N]
   std::vector<double> h_lst;                  // [T][N]
@@ -55,6 +63,8 @@ struct vbsky_layout {
   vbsky::Op* d_up = nullptr;
   vbsky::Op* d_down = nullptr;
   int32_t* d_down_nodes = nullptr;
+  int32_t* d_msg_rows = nullptr;
+  int32_t* d_msg_start = nullptr;
   int32_t* d_child_parent = nullptr;
   double* d_lst = nullptr;
   double* d_sample_times = nullptr;
@@ -67,8 +77,12 @@ struct vbsky_layout {
 struct vbsky_tips {
   int32_t T = 0, n = 0;
   int64_t S = 0;        // patterns per tree as given
-  int64_t S_pad = 0;    // padded to the kernel's tile multiple
-  uint8_t* d_codes = nullptr;  // [T][n][S_pad] code ranks (see tips.cu), tip-major / site-minor
+  int64_t S_pad = 0;    // padded to a multiple of kTile
+  int32_t tiles = 0;    // S_pad / kTile
+  // Code ranks (see tips.cu) in the order the two passes consume them, tile-major:
+  // [T][tiles][2(n-1)][kTile]; row 2s / 2s+1 = child a / b of schedule step s (filler for internal children).
+  uint8_t* d_codes_up = nullptr;
+  uint8_t* d_codes_dn = nullptr;
   double* d_counts = nullptr;  // [T][S_pad], 0 on padding
   int device = -1;
 };

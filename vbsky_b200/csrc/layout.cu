@@ -45,8 +45,8 @@ struct SlotPool {
 };
 
 // Build both schedules of one tree.  pc = parent_child [N][2].
-int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, int* depth_up,
-               int* depth_down) {
+int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, int32_t* msg_rows,
+               int32_t* msg_start, int* depth_up, int* depth_down) {
   const int N = 2 * n - 1, root = N - 1;
   auto internal = [n](int v) { return v >= n; };
 
@@ -95,7 +95,8 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
       if (internal(b)) sb = slot_of[b], pool.release(sb);
       if (v != root) so = pool.alloc(), slot_of[v] = so;
       if (so != 0xff && so >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
-      up[step] = Op{a, b, v, sa | (sb << 8) | (so << 16)};
+      up[step] = Op{a | (b << 16), v, sa | (sb << 8) | (so << 16),
+                    (internal(a) ? 0 : 1) | (internal(b) ? 0 : 2) | (v == root ? 4 : 0)};
       up_row[v] = step;
       ++step;
       st.pop_back();
@@ -128,10 +129,11 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
     st.push_back(root);
     SlotPool pool;
     std::fill(slot_of.begin(), slot_of.end(), -1);
-    int step = 0;
+    int step = 0, nmsg = 0;
     while (!st.empty()) {
       const int v = st.back();
       st.pop_back();
+      if (step % kChunkSteps == 0) msg_start[step / kChunkSteps] = nmsg;
       const int a = pc[2 * v + firstd[v]], b = pc[2 * v + 1 - firstd[v]];
       int sp = 0xff, sa = 0xff, sb = 0xff;
       if (v != root) sp = slot_of[v], pool.release(sp);
@@ -140,7 +142,9 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
       if ((sa != 0xff && sa >= 0xff) || (sb != 0xff && sb >= 0xff))
         return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
       const int ra = internal(a) ? up_row[a] : 0xffff, rb = internal(b) ? up_row[b] : 0xffff;
-      down[step] = Op{a | (b << 16), ra | (rb << 16), sp | (sa << 8) | (sb << 16), v};
+      down[step] = Op{a | (b << 16), v, sp | (sa << 8) | (sb << 16), (internal(a) ? 0 : 1) | (internal(b) ? 0 : 2)};
+      if (internal(a)) msg_rows[nmsg++] = ra;
+      if (internal(b)) msg_rows[nmsg++] = rb;
       down_nodes[2 * step] = a;
       down_nodes[2 * step + 1] = b;
       ++step;
@@ -148,6 +152,7 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
       if (internal(a)) st.push_back(a);  // a is expanded next
     }
     if (step != n - 1) return set_error(VBSKY_EINVAL, "internal error: down schedule has %d steps", step);
+    msg_start[(n - 1 + kChunkSteps - 1) / kChunkSteps] = nmsg;
     *depth_down = std::max(pool.high, 1);
   }
   return VBSKY_OK;
@@ -179,6 +184,8 @@ extern "C" void vbsky_layout_destroy(vbsky_layout* lay) {
   cudaFree(lay->d_up);
   cudaFree(lay->d_down);
   cudaFree(lay->d_down_nodes);
+  cudaFree(lay->d_msg_rows);
+  cudaFree(lay->d_msg_start);
   cudaFree(lay->d_child_parent);
   cudaFree(lay->d_lst);
   cudaFree(lay->d_sample_times);
@@ -203,6 +210,9 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   lay->h_up.resize((size_t)T * (n - 1));
   lay->h_down.resize((size_t)T * (n - 1));
   lay->h_down_nodes.resize((size_t)T * (2 * n - 2));
+  const int nchunks = (n - 1 + kChunkSteps - 1) / kChunkSteps;
+  lay->h_msg_rows.assign((size_t)T * std::max(n - 2, 1), 0);
+  lay->h_msg_start.assign((size_t)T * (nchunks + 1), 0);
   lay->h_child_parent.assign(child_parent, child_parent + (size_t)T * N);
   lay->h_siblings.assign((size_t)T * N, -1);
   lay->h_lst.assign((size_t)T * N, 0.0);
@@ -238,7 +248,8 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
 
     int du = 0, dd = 0;
     rc = build_tree(n, pc, &lay->h_up[(size_t)t * (n - 1)], &lay->h_down[(size_t)t * (n - 1)],
-                    &lay->h_down_nodes[(size_t)t * (2 * n - 2)], &du, &dd);
+                    &lay->h_down_nodes[(size_t)t * (2 * n - 2)], &lay->h_msg_rows[(size_t)t * std::max(n - 2, 1)],
+                    &lay->h_msg_start[(size_t)t * (nchunks + 1)], &du, &dd);
     if (rc != VBSKY_OK) break;
     lay->depth_up = std::max(lay->depth_up, du);
     lay->depth_down = std::max(lay->depth_down, dd);
@@ -301,6 +312,8 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   VB_UP(d_up, h_up)
   VB_UP(d_down, h_down)
   VB_UP(d_down_nodes, h_down_nodes)
+  VB_UP(d_msg_rows, h_msg_rows)
+  VB_UP(d_msg_start, h_msg_start)
   VB_UP(d_child_parent, h_child_parent)
   VB_UP(d_lst, h_lst)
   VB_UP(d_sample_times, h_sample_times)

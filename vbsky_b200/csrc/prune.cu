@@ -4,44 +4,68 @@
 // (prune.py:134-150) of the reference for every (tree, sample) unit at once.
 //
 // Design (DESIGN.md "Pruning kernel"):
-//   * one persistent CTA per resident slot; a work item is (unit, tile of TILE site patterns);
-//     one thread owns one site pattern for the whole tree walk;
-//   * P(t) = U exp(Lambda t) U^-1 is built once per (unit, branch) by transition_kernel, not per
-//     site as the reference does inside its vmap (substitution.py:64-70);
+//   * persistent, warp-specialised CTAs.  A work item is (unit, tile of kTile site patterns); four
+//     consumer warps own one site pattern per thread for the whole tree walk, a fifth (producer)
+//     warp streams everything the walk needs into shared-memory rings with cp.async.bulk (the
+//     1-D TMA path) completing on mbarriers: per-step records {op, P(t) matrices}, the tip codes of
+//     the step and -- in the down pass -- the children's messages from the CTA-private scratch.
+//     The math loop therefore never waits on a global load;
+//   * P(t) = U exp(Lambda t) U^-1 is built once per (unit, branch) by tables_kernel, in schedule
+//     order, not per site as the reference does inside its vmap (substitution.py:64-70);
 //   * the walk follows the layout's depth-first schedules, so the live "message" vectors
 //     (clip(P(t_c) post_c), the quantity both passes actually consume) sit in a small
-//     shared-memory stack; the up pass streams each internal node's message to a CTA-private
-//     HBM scratch row once and the down pass streams it back once.  pre vectors never leave
-//     the SM.  Value-only evaluation touches no scratch at all;
+//     shared-memory stack; the up pass streams each internal node's message to scratch once and
+//     the down pass streams it back once.  pre vectors never leave the SM.  Value-only evaluation
+//     touches no scratch at all;
 //   * per-site scale factors are accumulated as mantissa x 2^exponent (one log per site instead
 //     of one per node, prune.py:37), and the gradient uses the scale-free form of eq. (9),
 //       g_c = (w^T Q m_c) / (w^T m_c),  w = pre_parent (.) m_sibling,
 //     which equals prune.py:146-148 whenever the 1e-40 clips are inactive;
+//   * the clips of substitution.py:70 are applied literally only for units in which they can be
+//     active at all (some P(t) entry below 1e-20, i.e. a branch length of ~0); tables_kernel
+//     decides per unit.  Otherwise every clipped quantity is provably >= 1e-40 and <= 1 + few ulp;
 //   * branch gradients are reduced over the tile's sites through a transposed shared-memory
-//     staging buffer (1 add per value instead of a 5-step shuffle tree), written as per-tile
-//     partials and summed in a fixed order by finalize_kernel (bitwise reproducible).
+//     staging buffer, written as per-tile partials and summed in a fixed order by finalize_kernel
+//     (bitwise reproducible).
 #include <cmath>
 
 #include "common.h"
 
 namespace vbsky {
 
-constexpr int TILE = 128;  // site patterns per CTA tile == threads per CTA
-constexpr int GCH = 16;    // branch gradients staged per reduction round
+constexpr int TILE = kTile;
+constexpr int NCW = TILE / 32;        // consumer warps
+constexpr int THREADS = TILE + 32;    // + producer warp
+constexpr int CH = kChunkSteps;       // steps per ring stage
+constexpr int NST = 3;                // step-chunk ring stages
+constexpr int NMS = 4;                // message ring slots
+constexpr int UPREC = 50;             // doubles per up-step record:   op(2) Pa(16) Pb(16) Pp(16)
+constexpr int DNREC = 66;             // doubles per down-step record: op(2) Pa(16) Pb(16) QPa(16) QPb(16)
+constexpr int CODE_ROW = TILE;        // bytes of tip codes per (step, child)
+constexpr int STAGE_BYTES = CH * DNREC * 8 + 2 * CH * CODE_ROW;
+constexpr int STAGE_CODES = CH * DNREC * 8;  // byte offset of the code rows inside a stage
+constexpr int MSG_BYTES = 4 * TILE * 8;
+constexpr int GCH = 16;               // branch gradients staged per reduction round
 constexpr int GROW = TILE + 1;
+constexpr int OFF_STAGE = 128;
+constexpr int OFF_MSG = OFF_STAGE + ((NST * STAGE_BYTES + 127) / 128) * 128;
+constexpr int OFF_STK = OFF_MSG + NMS * MSG_BYTES;
+static_assert(STAGE_BYTES % 16 == 0 && (UPREC * 8) % 16 == 0 && (DNREC * 8) % 16 == 0, "bulk copies need 16-byte granularity");
 
 struct PruneParams {
-  const Op* up;
-  const Op* down;
-  const uint8_t* codes;
-  const double* counts;
+  const double* uptab;    // [U][n-1][UPREC]
+  const double* dntab;    // [U][n-1][DNREC]
+  const uint32_t* flags;  // [U] bit0: clips may be active
+  const uint8_t* codes_up;
+  const uint8_t* codes_dn;  // [T][tiles][2(n-1)][TILE]
+  const double* counts;     // [T][S_pad]
   const int32_t* unit_tree;
-  const double* ptab;   // [U][2n-2][16]
-  const double* qptab;  // [U][n][16]
-  double* scratch;      // [grid][n-1][4][TILE]
-  double* site_ll;      // [U][S] or null
-  double* ll_part;      // [U][tiles]
-  double* g_part;       // [U][tiles][2n-2]
+  const int32_t* msg_rows;   // [T][max(n-2,1)]
+  const int32_t* msg_start;  // [T][nchunks+1]
+  double* scratch;           // [grid][n-1][4][TILE]
+  double* site_ll;           // [U][S] or null
+  double* ll_part;           // [U][tiles]
+  double* g_part;            // [U][tiles][2n-2]
   double Q[16];
   double pi[4];
   int n, U, tiles, depth;
@@ -50,94 +74,137 @@ struct PruneParams {
 
 __device__ __constant__ uint8_t kRankToMask[16] = {1, 2, 4, 8, 15, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 0};
 
-__device__ __forceinline__ double clip01(double x) {
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TILE) : "memory"); }
+
+template <bool CLIP>
+__device__ __forceinline__ double clipv(double x) {
   // jnp.clip(ret, 1e-40, 1.0) of substitution.py:70
-  return fmin(fmax(x, 1e-40), 1.0);
+  return CLIP ? fmin(fmax(x, 1e-40), 1.0) : x;
 }
 
-__device__ __forceinline__ void load16(const double* __restrict__ p, double (&M)[16]) {
+__device__ __forceinline__ void lds16(const double* p, double (&M)[16]) {
   const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const double2 v = __ldg(q + i);
+    const double2 v = q[i];
     M[2 * i] = v.x, M[2 * i + 1] = v.y;
   }
 }
 
-// Message of a tip: clip(P(t) e_mask) where e_mask is the 0/1 tip partial (substitution.py:10-35).
-// rank < 4 is a single column of P.
-__device__ __forceinline__ void tip_columns(const double* __restrict__ M, int rank, bool all_simple, double (&out)[4]) {
+// Columns of a 4x4 matrix selected by a tip's state set: M e_mask (substitution.py:10-35 partials).
+// rank < 4 is a single column.
+__device__ __forceinline__ void tip_columns(const double* M, int rank, bool all_simple, double (&out)[4]) {
   if (all_simple) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) out[i] = __ldg(M + i * 4 + rank);
+    for (int i = 0; i < 4; ++i) out[i] = M[i * 4 + rank];
   } else {
     const int mask = kRankToMask[rank];
+    double A[16];
+    lds16(M, A);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double v = __ldg(M + i * 4 + j);
-        s += ((mask >> j) & 1) ? v : 0.0;
-      }
+      for (int j = 0; j < 4; ++j) s += ((mask >> j) & 1) ? A[i * 4 + j] : 0.0;
       out[i] = s;
     }
   }
 }
 
-template <bool WANT_GRAD>
-__global__ void __launch_bounds__(TILE, 4) prune_kernel(const PruneParams p) {
-  extern __shared__ double smem[];
-  double* stk = smem;                              // [depth][4][TILE]
-  double* gst = stk + (size_t)p.depth * 4 * TILE;  // [GCH][GROW]
-  double* red = gst + GCH * GROW;                  // [TILE/GCH][GCH] and block reductions
+struct RingState {
+  uint32_t cst = 0, cph = 0;  // step-chunk ring stage / phase
+  uint32_t mst = 0, mph = 0;  // message ring slot / phase
+  __device__ __forceinline__ void adv_c() {
+    if (++cst == NST) cst = 0, cph ^= 1;
+  }
+  __device__ __forceinline__ void adv_m() {
+    if (++mst == NMS) mst = 0, mph ^= 1;
+  }
+};
+
+// Barrier slots (8 bytes each) at the start of dynamic shared memory.
+__device__ __forceinline__ uint32_t bar_full_c(uint32_t base, uint32_t s) { return base + 8 * s; }
+__device__ __forceinline__ uint32_t bar_empty_c(uint32_t base, uint32_t s) { return base + 8 * (NST + s); }
+__device__ __forceinline__ uint32_t bar_full_m(uint32_t base, uint32_t s) { return base + 8 * (2 * NST + s); }
+__device__ __forceinline__ uint32_t bar_empty_m(uint32_t base, uint32_t s) { return base + 8 * (2 * NST + NMS + s); }
+__device__ __forceinline__ uint32_t bar_up_done(uint32_t base) { return base + 8 * (2 * NST + 2 * NMS); }
+
+// One work item for the four consumer warps.
+template <bool WANT_GRAD, bool CLIP>
+__device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char* smem, RingState& rs, int u, int tile,
+                                             int t, double* myscr) {
+  const uint32_t bars = smem_u32(smem);
+  double* stk = reinterpret_cast<double*>(smem + OFF_STK);  // [depth][4][TILE]
+  double* gst = stk + (size_t)p.depth * 4 * TILE;           // [GCH][GROW]
+  double* red = gst + GCH * GROW;                           // [TILE]
   const int tid = threadIdx.x;
-  const int n = p.n, root = 2 * n - 2;
-  const long long items = (long long)p.U * p.tiles;
-  double* myscr = p.scratch + (size_t)blockIdx.x * (n - 1) * 4 * TILE + tid;
+  const int lane = tid & 31;
+  const int n = p.n;
+  const int nsteps = n - 1;
+  const long long s = (long long)tile * TILE + tid;
+  const double cnt = p.counts[(size_t)t * p.S_pad + s];
 
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int u = (int)(item / p.tiles);
-    const int tile = (int)(item - (long long)u * p.tiles);
-    const int t = p.unit_tree[u];
-    const long long s = (long long)tile * TILE + tid;
-    const Op* up = p.up + (size_t)t * (n - 1);
-    const uint8_t* codes = p.codes + (size_t)t * n * p.S_pad + s;
-    const double* ptab = p.ptab + (size_t)u * (2 * n - 2) * 16;
-    const double cnt = p.counts[(size_t)t * p.S_pad + s];
-
-    // ------------------------------------------------------------------ up pass (prune.py:15-49)
-    double sc = 1.0;
-    int ex = 0;
-    double ll_site = 0.0;
-    for (int step = 0; step < n - 1; ++step) {
-      const Op op = up[step];
-      const int a = op.x, b = op.y, par = op.z;
+  // ------------------------------------------------------------------ up pass (prune.py:15-49)
+  double sc = 1.0;
+  int ex = 0;
+  double ll_site = 0.0;
+  for (int c0 = 0; c0 < nsteps; c0 += CH) {
+    const unsigned char* stage = smem + OFF_STAGE + rs.cst * STAGE_BYTES;
+    mbar_wait(bar_full_c(bars, rs.cst), rs.cph);
+    const int cn = min(CH, nsteps - c0);
+    for (int k = 0; k < cn; ++k) {
+      const double* rec = reinterpret_cast<const double*>(stage) + k * UPREC;
+      const int4 op = *reinterpret_cast<const int4*>(rec);
+      const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + tid;
       double ma[4], mb[4];
-      if (a < n) {
-        const int r = codes[(size_t)a * p.S_pad];
-        tip_columns(ptab + a * 16, r, __all_sync(0xffffffffu, r < 4), ma);
+      if (op.w & 1) {
+        const int r = crow[0];
+        tip_columns(rec + 2, r, __all_sync(0xffffffffu, r < 4), ma);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ma[i] = clip01(ma[i]);
+        for (int i = 0; i < 4; ++i) ma[i] = clipv<CLIP>(ma[i]);
       } else {
-        const double* src = stk + (size_t)(op.w & 0xff) * 4 * TILE + tid;
+        const double* src = stk + (op.z & 0xff) * (4 * TILE) + tid;
 #pragma unroll
         for (int i = 0; i < 4; ++i) ma[i] = src[i * TILE];
       }
-      if (b < n) {
-        const int r = codes[(size_t)b * p.S_pad];
-        tip_columns(ptab + b * 16, r, __all_sync(0xffffffffu, r < 4), mb);
+      if (op.w & 2) {
+        const int r = crow[CODE_ROW];
+        tip_columns(rec + 18, r, __all_sync(0xffffffffu, r < 4), mb);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mb[i] = clip01(mb[i]);
+        for (int i = 0; i < 4; ++i) mb[i] = clipv<CLIP>(mb[i]);
       } else {
-        const double* src = stk + (size_t)((op.w >> 8) & 0xff) * 4 * TILE + tid;
+        const double* src = stk + ((op.z >> 8) & 0xff) * (4 * TILE) + tid;
 #pragma unroll
         for (int i = 0; i < 4; ++i) mb[i] = src[i * TILE];
       }
       double pr[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) pr[i] = ma[i] * mb[i];
-      if (par == root) {
+      if (op.w & 4) {
         // log(post[root] . pi) + const[root]  (prune.py:131) with post = Pprod / c folded in
         const double like = (pr[0] * p.pi[0] + pr[1] * p.pi[1]) + (pr[2] * p.pi[2] + pr[3] * p.pi[3]);
         ll_site = log(like * sc) + (double)ex * 0.6931471805599453094;
@@ -155,77 +222,100 @@ __global__ void __launch_bounds__(TILE, 4) prune_kernel(const PruneParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) post[i] = pr[i] * inv;
         double M[16];
-        load16(ptab + par * 16, M);
-        double* dst = stk + (size_t)((op.w >> 16) & 0xff) * 4 * TILE + tid;
+        lds16(rec + 34, M);
+        double* dst = stk + ((op.z >> 16) & 0xff) * (4 * TILE) + tid;
+        double* gdst = myscr + (size_t)(c0 + k) * (4 * TILE);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const double v = clip01(M[i * 4 + 0] * post[0] + M[i * 4 + 1] * post[1] + M[i * 4 + 2] * post[2] + M[i * 4 + 3] * post[3]);
+          const double v = clipv<CLIP>(M[i * 4 + 0] * post[0] + M[i * 4 + 1] * post[1] + M[i * 4 + 2] * post[2] + M[i * 4 + 3] * post[3]);
           dst[i * TILE] = v;
-          if (WANT_GRAD) __stcg(myscr + ((size_t)step * 4 + i) * TILE, v);
+          if (WANT_GRAD) __stcg(gdst + i * TILE, v);
         }
       }
     }
-    if (p.site_ll != nullptr && s < p.S) p.site_ll[(size_t)u * p.S + s] = ll_site;
-    {
-      // sum_s counts[s] * ll_s over the tile (bdsky.py:341)
-      double v = cnt * ll_site;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty_c(bars, rs.cst));
+    rs.adv_c();
+  }
+  if (WANT_GRAD) {
+    // make this thread's scratch stores visible to the producer's async-proxy reads, then signal
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_up_done(bars));
+  }
+  if (p.site_ll != nullptr && s < p.S) p.site_ll[(size_t)u * p.S + s] = ll_site;
+  {
+    // sum_s counts[s] * ll_s over the tile (bdsky.py:341)
+    double v = cnt * ll_site;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      __syncthreads();
-      if ((tid & 31) == 0) red[tid >> 5] = v;
-      __syncthreads();
-      if (tid == 0) {
-        double tot = 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    consumer_bar();
+    if (lane == 0) red[tid >> 5] = v;
+    consumer_bar();
+    if (tid == 0) {
+      double tot = 0.0;
 #pragma unroll
-        for (int w = 0; w < TILE / 32; ++w) tot += red[w];
-        p.ll_part[(size_t)u * p.tiles + tile] = tot;
-      }
+      for (int w = 0; w < NCW; ++w) tot += red[w];
+      p.ll_part[(size_t)u * p.tiles + tile] = tot;
     }
-    if (!WANT_GRAD) continue;
+  }
+  if (!WANT_GRAD) return;
 
-    // ------------------------------------------- down pass (prune.py:52-96) + eq. (9) (prune.py:146)
-    const Op* down = p.down + (size_t)t * (n - 1);
-    const double* qptab = p.qptab + (size_t)u * n * 16;
-    double* gout = p.g_part + ((size_t)u * p.tiles + tile) * (2 * n - 2);
-    for (int step = 0; step < n - 1; ++step) {
-      const Op op = down[step];
-      const int a = op.x & 0xffff, b = (op.x >> 16) & 0xffff;
+  // ------------------------------------------- down pass (prune.py:52-96) + eq. (9) (prune.py:146)
+  double* gout = p.g_part + ((size_t)u * p.tiles + tile) * (2 * n - 2);
+  for (int c0 = 0; c0 < nsteps; c0 += CH) {
+    const unsigned char* stage = smem + OFF_STAGE + rs.cst * STAGE_BYTES;
+    mbar_wait(bar_full_c(bars, rs.cst), rs.cph);
+    const int cn = min(CH, nsteps - c0);
+    for (int k = 0; k < cn; ++k) {
+      const int step = c0 + k;
+      const double* rec = reinterpret_cast<const double*>(stage) + k * DNREC;
+      const int4 op = *reinterpret_cast<const int4*>(rec);
+      const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + tid;
       const int sp = op.z & 0xff;
       double pre[4];
       if (sp == 0xff) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) pre[i] = p.pi[i];  // pre[root] = pi (prune.py:88)
       } else {
-        const double* src = stk + (size_t)sp * 4 * TILE + tid;
+        const double* src = stk + sp * (4 * TILE) + tid;
 #pragma unroll
         for (int i = 0; i < 4; ++i) pre[i] = src[i * TILE];
       }
       double ma[4], mb[4], qa[4], qb[4];
-      if (a < n) {
-        const int r = codes[(size_t)a * p.S_pad];
+      if (op.w & 1) {
+        const int r = crow[0];
         const bool simple = __all_sync(0xffffffffu, r < 4);
-        tip_columns(ptab + a * 16, r, simple, ma);
-        tip_columns(qptab + a * 16, r, simple, qa);
+        tip_columns(rec + 2, r, simple, ma);
+        tip_columns(rec + 34, r, simple, qa);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ma[i] = clip01(ma[i]);
+        for (int i = 0; i < 4; ++i) ma[i] = clipv<CLIP>(ma[i]);
       } else {
-        const double* src = myscr + (size_t)(op.y & 0xffff) * 4 * TILE;
+        mbar_wait(bar_full_m(bars, rs.mst), rs.mph);
+        const double* src = reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + tid;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ma[i] = __ldcg(src + i * TILE);
+        for (int i = 0; i < 4; ++i) ma[i] = src[i * TILE];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty_m(bars, rs.mst));
+        rs.adv_m();
 #pragma unroll
         for (int i = 0; i < 4; ++i) qa[i] = p.Q[i * 4 + 0] * ma[0] + p.Q[i * 4 + 1] * ma[1] + p.Q[i * 4 + 2] * ma[2] + p.Q[i * 4 + 3] * ma[3];
       }
-      if (b < n) {
-        const int r = codes[(size_t)b * p.S_pad];
+      if (op.w & 2) {
+        const int r = crow[CODE_ROW];
         const bool simple = __all_sync(0xffffffffu, r < 4);
-        tip_columns(ptab + b * 16, r, simple, mb);
-        tip_columns(qptab + b * 16, r, simple, qb);
+        tip_columns(rec + 18, r, simple, mb);
+        tip_columns(rec + 50, r, simple, qb);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mb[i] = clip01(mb[i]);
+        for (int i = 0; i < 4; ++i) mb[i] = clipv<CLIP>(mb[i]);
       } else {
-        const double* src = myscr + (size_t)((op.y >> 16) & 0xffff) * 4 * TILE;
+        mbar_wait(bar_full_m(bars, rs.mst), rs.mph);
+        const double* src = reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + tid;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mb[i] = __ldcg(src + i * TILE);
+        for (int i = 0; i < 4; ++i) mb[i] = src[i * TILE];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty_m(bars, rs.mst));
+        rs.adv_m();
 #pragma unroll
         for (int i = 0; i < 4; ++i) qb[i] = p.Q[i * 4 + 0] * mb[0] + p.Q[i * 4 + 1] * mb[1] + p.Q[i * 4 + 2] * mb[2] + p.Q[i * 4 + 3] * mb[3];
       }
@@ -240,88 +330,203 @@ __global__ void __launch_bounds__(TILE, 4) prune_kernel(const PruneParams p) {
       gst[gslot * GROW + tid] = ga;
       gst[(gslot + 1) * GROW + tid] = gb;
 
-      if (a >= n) {
+      if (!(op.w & 1)) {
         double M[16];
-        load16(ptab + a * 16, M);
+        lds16(rec + 2, M);
         double B[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) B[v] = clip01(wa[0] * M[0 * 4 + v] + wa[1] * M[1 * 4 + v] + wa[2] * M[2 * 4 + v] + wa[3] * M[3 * 4 + v]);
+        for (int v = 0; v < 4; ++v) B[v] = clipv<CLIP>(wa[0] * M[0 * 4 + v] + wa[1] * M[1 * 4 + v] + wa[2] * M[2 * 4 + v] + wa[3] * M[3 * 4 + v]);
         const double inv = 1.0 / ((B[0] + B[1]) + (B[2] + B[3]));
-        double* dst = stk + (size_t)((op.z >> 8) & 0xff) * 4 * TILE + tid;
+        double* dst = stk + ((op.z >> 8) & 0xff) * (4 * TILE) + tid;
 #pragma unroll
         for (int v = 0; v < 4; ++v) dst[v * TILE] = B[v] * inv;
       }
-      if (b >= n) {
+      if (!(op.w & 2)) {
         double M[16];
-        load16(ptab + b * 16, M);
+        lds16(rec + 18, M);
         double B[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) B[v] = clip01(wb[0] * M[0 * 4 + v] + wb[1] * M[1 * 4 + v] + wb[2] * M[2 * 4 + v] + wb[3] * M[3 * 4 + v]);
+        for (int v = 0; v < 4; ++v) B[v] = clipv<CLIP>(wb[0] * M[0 * 4 + v] + wb[1] * M[1 * 4 + v] + wb[2] * M[2 * 4 + v] + wb[3] * M[3 * 4 + v]);
         const double inv = 1.0 / ((B[0] + B[1]) + (B[2] + B[3]));
-        double* dst = stk + (size_t)((op.z >> 16) & 0xff) * 4 * TILE + tid;
+        double* dst = stk + ((op.z >> 16) & 0xff) * (4 * TILE) + tid;
 #pragma unroll
         for (int v = 0; v < 4; ++v) dst[v * TILE] = B[v] * inv;
       }
 
-      const bool last = step == n - 2;
-      if (gslot + 2 == GCH || last) {
+      if (gslot + 2 == GCH || step == nsteps - 1) {
         // transposed reduction of the staged chunk over the tile's sites
-        const int nval = gslot + 2;  // valid staged rows
-        __syncthreads();
+        const int nval = gslot + 2;
+        consumer_bar();
         const int r = tid & (GCH - 1), q = tid / GCH;
         double acc = 0.0;
         if (r < nval) {
           const double* row = gst + r * GROW + q * GCH;
 #pragma unroll
-          for (int k = 0; k < GCH; ++k) acc += row[k];
+          for (int kk = 0; kk < GCH; ++kk) acc += row[kk];
         }
         red[q * GCH + r] = acc;
-        __syncthreads();
+        consumer_bar();
         if (tid < nval) {
           double tot = 0.0;
 #pragma unroll
-          for (int k = 0; k < TILE / GCH; ++k) tot += red[k * GCH + tid];
+          for (int kk = 0; kk < TILE / GCH; ++kk) tot += red[kk * GCH + tid];
           gout[2 * step + 2 - nval + tid] = tot;
         }
       }
     }
-    __syncthreads();  // red / gst are reused by the next item
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty_c(bars, rs.cst));
+    rs.adv_c();
+  }
+  consumer_bar();  // red / gst are reused by the next item
+}
+
+template <bool WANT_GRAD>
+__global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t bars = smem_u32(smem);
+  const int tid = threadIdx.x;
+  const int n = p.n;
+  const int nsteps = n - 1;
+  const long long items = (long long)p.U * p.tiles;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) mbar_init(bar_full_c(bars, i), 1), mbar_init(bar_empty_c(bars, i), NCW);
+    for (int i = 0; i < NMS; ++i) mbar_init(bar_full_m(bars, i), 1), mbar_init(bar_empty_m(bars, i), NCW);
+    mbar_init(bar_up_done(bars), NCW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  RingState rs;
+  const unsigned char* scr_base = reinterpret_cast<const unsigned char*>(p.scratch) + (size_t)blockIdx.x * nsteps * MSG_BYTES;
+
+  if (tid >= TILE) {
+    // =============================================================== producer warp (one lane)
+    if (tid != TILE) return;
+    uint32_t up_phase = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+      const int u = (int)(item / p.tiles);
+      const int tile = (int)(item - (long long)u * p.tiles);
+      const int t = p.unit_tree[u];
+      const unsigned char* utab = reinterpret_cast<const unsigned char*>(p.uptab) + (size_t)u * nsteps * (UPREC * 8);
+      const unsigned char* cup = p.codes_up + ((size_t)t * p.tiles + tile) * (size_t)(2 * nsteps) * CODE_ROW;
+      for (int c0 = 0; c0 < nsteps; c0 += CH) {
+        const int cn = min(CH, nsteps - c0);
+        mbar_wait(bar_empty_c(bars, rs.cst), rs.cph ^ 1);
+        const uint32_t dst = smem_u32(smem + OFF_STAGE + rs.cst * STAGE_BYTES);
+        const uint32_t full = bar_full_c(bars, rs.cst);
+        mbar_expect_tx(full, cn * (UPREC * 8 + 2 * CODE_ROW));
+        bulk_g2s(dst, utab + (size_t)c0 * (UPREC * 8), cn * UPREC * 8, full);
+        bulk_g2s(dst + STAGE_CODES, cup + (size_t)c0 * 2 * CODE_ROW, cn * 2 * CODE_ROW, full);
+        rs.adv_c();
+      }
+      if (!WANT_GRAD) continue;
+      const unsigned char* dtab = reinterpret_cast<const unsigned char*>(p.dntab) + (size_t)u * nsteps * (DNREC * 8);
+      const unsigned char* cdn = p.codes_dn + ((size_t)t * p.tiles + tile) * (size_t)(2 * nsteps) * CODE_ROW;
+      const int nchunks = (nsteps + CH - 1) / CH;
+      const int32_t* mrows = p.msg_rows + (size_t)t * max(n - 2, 1);
+      const int32_t* mstart = p.msg_start + (size_t)t * (nchunks + 1);
+      mbar_wait(bar_up_done(bars), up_phase);  // every consumer warp has finished (and fenced) its scratch stores
+      up_phase ^= 1;
+      int mi = 0;
+      for (int c0 = 0, c = 0; c0 < nsteps; c0 += CH, ++c) {
+        const int cn = min(CH, nsteps - c0);
+        mbar_wait(bar_empty_c(bars, rs.cst), rs.cph ^ 1);
+        const uint32_t dst = smem_u32(smem + OFF_STAGE + rs.cst * STAGE_BYTES);
+        const uint32_t full = bar_full_c(bars, rs.cst);
+        mbar_expect_tx(full, cn * (DNREC * 8 + 2 * CODE_ROW));
+        bulk_g2s(dst, dtab + (size_t)c0 * (DNREC * 8), cn * DNREC * 8, full);
+        bulk_g2s(dst + STAGE_CODES, cdn + (size_t)c0 * 2 * CODE_ROW, cn * 2 * CODE_ROW, full);
+        rs.adv_c();
+        const int mend = mstart[c + 1];
+        for (; mi < mend; ++mi) {
+          const int row = mrows[mi];
+          mbar_wait(bar_empty_m(bars, rs.mst), rs.mph ^ 1);
+          const uint32_t mfull = bar_full_m(bars, rs.mst);
+          mbar_expect_tx(mfull, MSG_BYTES);
+          bulk_g2s(smem_u32(smem + OFF_MSG + rs.mst * MSG_BYTES), scr_base + (size_t)row * MSG_BYTES, MSG_BYTES, mfull);
+          rs.adv_m();
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================================================= consumer warps
+  double* myscr = p.scratch + (size_t)blockIdx.x * nsteps * (4 * TILE) + tid;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int u = (int)(item / p.tiles);
+    const int tile = (int)(item - (long long)u * p.tiles);
+    const int t = p.unit_tree[u];
+    if (p.flags[u] & 1u)
+      consume_item<WANT_GRAD, true>(p, smem, rs, u, tile, t, myscr);
+    else
+      consume_item<WANT_GRAD, false>(p, smem, rs, u, tile, t, myscr);
   }
 }
 
-// P(t) = U diag(exp(d t)) Uinv per (unit, node) (substitution.py:61-62), and Q P(t) for tip branches.
-__global__ void transition_kernel(const double* __restrict__ bl, int U, int n, vbsky_subst_model mdl,
-                                  double* __restrict__ ptab, double* __restrict__ qptab) {
-  const int nb = 2 * n - 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)U * nb) return;
-  const int u = (int)(idx / nb), c = (int)(idx - (long long)u * nb);
-  const double t = bl[idx];
+// ------------------------------------------------------------------------------ transition tables
+struct TablesParams {
+  const double* bl;  // [U][2n-2]
+  const int32_t* unit_tree;
+  const Op* up;
+  const Op* down;  // [T][n-1]
+  double* uptab;
+  double* dntab;
+  uint32_t* flags;
+  vbsky_subst_model mdl;
+  int U, n, want_grad;
+};
+
+// P(t) = U diag(exp(d t)) Uinv (substitution.py:61-62); optionally Q P(t) = U diag(d exp(d t)) Uinv.
+__device__ __forceinline__ bool expm16(const vbsky_subst_model& m, double t, double* P, double* QP) {
   double e[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) e[k] = exp(t * mdl.d[k]);
-  double* out = ptab + idx * 16;
+  for (int k = 0; k < 4; ++k) e[k] = exp(t * m.d[k]);
+  bool small = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      double s = 0.0;
+      double s = 0.0, q = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s += mdl.P[i * 4 + k] * (e[k] * mdl.Pinv[k * 4 + j]);
-      out[i * 4 + j] = s;
-    }
-  if (c < n && qptab != nullptr) {
-    double* qo = qptab + ((size_t)u * n + c) * 16;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s += mdl.P[i * 4 + k] * (mdl.d[k] * e[k] * mdl.Pinv[k * 4 + j]);
-        qo[i * 4 + j] = s;
+      for (int k = 0; k < 4; ++k) {
+        const double w = m.P[i * 4 + k] * (e[k] * m.Pinv[k * 4 + j]);
+        s += w;
+        q += m.d[k] * w;
       }
+      P[i * 4 + j] = s;
+      if (QP) QP[i * 4 + j] = q;
+      small |= !(s >= 1e-20) || !(s <= 2.0);  // also catches NaN / inf
+    }
+  return small;
+}
+
+__global__ void tables_kernel(const TablesParams p) {
+  const int nsteps = p.n - 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)p.U * nsteps) return;
+  const int u = (int)(idx / nsteps), step = (int)(idx - (long long)u * nsteps);
+  const int t = p.unit_tree[u];
+  const double* bl = p.bl + (size_t)u * (2 * p.n - 2);
+  bool small = false;
+  {
+    const Op op = p.up[(size_t)t * nsteps + step];
+    double* rec = p.uptab + idx * UPREC;
+    *reinterpret_cast<int4*>(rec) = make_int4(op.x, op.y, op.z, op.w);
+    const int a = op.x & 0xffff, b = (op.x >> 16) & 0xffff;
+    if (op.w & 1) small |= expm16(p.mdl, bl[a], rec + 2, nullptr);
+    if (op.w & 2) small |= expm16(p.mdl, bl[b], rec + 18, nullptr);
+    if (!(op.w & 4)) small |= expm16(p.mdl, bl[op.y], rec + 34, nullptr);
   }
+  if (p.want_grad) {
+    const Op op = p.down[(size_t)t * nsteps + step];
+    double* rec = p.dntab + idx * DNREC;
+    *reinterpret_cast<int4*>(rec) = make_int4(op.x, op.y, op.z, op.w);
+    const int a = op.x & 0xffff, b = (op.x >> 16) & 0xffff;
+    small |= expm16(p.mdl, bl[a], rec + 2, (op.w & 1) ? rec + 34 : nullptr);
+    small |= expm16(p.mdl, bl[b], rec + 18, (op.w & 2) ? rec + 50 : nullptr);
+  }
+  if (small) atomicOr(p.flags + u, 1u);
 }
 
 // Fixed-order sums of the per-tile partials: ll[u] and dll_dbl[u][node].
@@ -348,7 +553,7 @@ __global__ void finalize_kernel(const double* __restrict__ ll_part, const double
 struct PruneConfig {
   int grid = 0, depth = 0, tiles = 0;
   size_t smem = 0;
-  size_t off_ptab = 0, off_qptab = 0, off_scratch = 0, off_llpart = 0, off_gpart = 0, total = 0;
+  size_t off_uptab = 0, off_dntab = 0, off_flags = 0, off_scratch = 0, off_llpart = 0, off_gpart = 0, total = 0;
 };
 
 static thread_local int64_t g_stats[8] = {0};
@@ -356,34 +561,31 @@ static thread_local int64_t g_stats[8] = {0};
 static int prune_config(const vbsky_layout* lay, const vbsky_tips* tips, int U, bool want_grad, PruneConfig* cfg) {
   const int n = lay->n;
   cfg->depth = want_grad ? std::max(lay->depth_up, lay->depth_down) : lay->depth_up;
-  cfg->smem = ((size_t)cfg->depth * 4 * TILE + (size_t)GCH * GROW + TILE) * sizeof(double);
-  cfg->tiles = (int)((tips->S + TILE - 1) / TILE);
-  int dev = 0, sms = 0, per_sm = 0;
+  cfg->smem = (size_t)OFF_STK + ((size_t)cfg->depth * 4 * TILE + (size_t)GCH * GROW + TILE) * sizeof(double);
+  cfg->tiles = tips->tiles;
+  int dev = 0, sms = 0, per_sm = 0, max_smem = 0;
   VB_CUDA(cudaGetDevice(&dev));
   VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  size_t max_smem = 0;
-  {
-    int v = 0;
-    VB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    max_smem = (size_t)v;
-  }
-  if (cfg->smem > max_smem)
-    return set_error(VBSKY_EINVAL, "tree needs %d live vectors (%zu B shared memory) but the device offers %zu B", cfg->depth, cfg->smem, max_smem);
+  VB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (cfg->smem > (size_t)max_smem)
+    return set_error(VBSKY_EINVAL, "tree needs %d live vectors (%zu B shared memory) but the device offers %d B", cfg->depth, cfg->smem, max_smem);
   if (want_grad) {
     VB_CUDA(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<true>, TILE, cfg->smem));
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<true>, THREADS, cfg->smem));
   } else {
     VB_CUDA(cudaFuncSetAttribute(prune_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<false>, TILE, cfg->smem));
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<false>, THREADS, cfg->smem));
   }
   if (per_sm < 1) return set_error(VBSKY_ECUDA, "pruning kernel cannot be resident (smem %zu B)", cfg->smem);
   const long long items = (long long)U * cfg->tiles;
-  cfg->grid = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
+  const long long slots = (long long)sms * per_sm;
+  cfg->grid = (int)std::min<long long>(slots, std::max<long long>(items, 1));
   auto align = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t off = 0;
-  cfg->off_ptab = off, off = align(off + (size_t)U * (2 * n - 2) * 16 * sizeof(double));
-  cfg->off_qptab = off, off = align(off + (want_grad ? (size_t)U * n * 16 * sizeof(double) : 0));
-  cfg->off_scratch = off, off = align(off + (want_grad ? (size_t)sms * per_sm * (n - 1) * 4 * TILE * sizeof(double) : 0));
+  cfg->off_uptab = off, off = align(off + (size_t)U * (n - 1) * UPREC * sizeof(double));
+  cfg->off_dntab = off, off = align(off + (want_grad ? (size_t)U * (n - 1) * DNREC * sizeof(double) : 0));
+  cfg->off_flags = off, off = align(off + (size_t)U * sizeof(uint32_t));
+  cfg->off_scratch = off, off = align(off + (want_grad ? (size_t)slots * (n - 1) * MSG_BYTES : 0));
   cfg->off_llpart = off, off = align(off + (size_t)U * cfg->tiles * sizeof(double));
   cfg->off_gpart = off, off = align(off + (want_grad ? (size_t)U * cfg->tiles * (2 * n - 2) * sizeof(double) : 0));
   cfg->total = off;
@@ -395,7 +597,10 @@ static int prune_config(const vbsky_layout* lay, const vbsky_tips* tips, int U, 
 using namespace vbsky;
 
 extern "C" size_t vbsky_prune_workspace_bytes(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, int32_t want_grad) {
-  if (!lay || !tips || U < 1) return 0;
+  if (!lay || !tips || U < 1) {
+    set_error(VBSKY_EINVAL, "bad argument to vbsky_prune_workspace_bytes");
+    return 0;
+  }
   PruneConfig cfg;
   if (prune_config(lay, tips, U, want_grad != 0, &cfg) != VBSKY_OK) return 0;
   return cfg.total;
@@ -418,12 +623,24 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
   if (ws_bytes < cfg.total) return set_error(VBSKY_ENOMEM, "workspace too small: %zu < %zu bytes", ws_bytes, cfg.total);
   const int n = lay->n;
   char* base = (char*)ws;
+
+  TablesParams tp;
+  tp.bl = bl, tp.unit_tree = unit_tree, tp.up = lay->d_up, tp.down = lay->d_down;
+  tp.uptab = (double*)(base + cfg.off_uptab), tp.dntab = (double*)(base + cfg.off_dntab);
+  tp.flags = (uint32_t*)(base + cfg.off_flags);
+  tp.mdl = *model, tp.U = U, tp.n = n, tp.want_grad = want_grad;
+  VB_CUDA(cudaMemsetAsync(tp.flags, 0, (size_t)U * sizeof(uint32_t), stream));
+  {
+    const long long tot = (long long)U * (n - 1);
+    tables_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, stream>>>(tp);
+    VB_CUDA(cudaGetLastError());
+  }
+
   PruneParams p;
-  p.up = lay->d_up, p.down = lay->d_down;
-  p.codes = tips->d_codes, p.counts = tips->d_counts;
+  p.uptab = tp.uptab, p.dntab = tp.dntab, p.flags = tp.flags;
+  p.codes_up = tips->d_codes_up, p.codes_dn = tips->d_codes_dn, p.counts = tips->d_counts;
   p.unit_tree = unit_tree;
-  p.ptab = (double*)(base + cfg.off_ptab);
-  p.qptab = want_grad ? (double*)(base + cfg.off_qptab) : nullptr;
+  p.msg_rows = lay->d_msg_rows, p.msg_start = lay->d_msg_start;
   p.scratch = (double*)(base + cfg.off_scratch);
   p.site_ll = site_ll;
   p.ll_part = (double*)(base + cfg.off_llpart);
@@ -432,16 +649,10 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
   for (int i = 0; i < 4; ++i) p.pi[i] = model->pi[i];
   p.n = n, p.U = U, p.tiles = cfg.tiles, p.depth = cfg.depth;
   p.S = tips->S, p.S_pad = tips->S_pad;
-
-  {
-    const long long tot = (long long)U * (2 * n - 2);
-    transition_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, stream>>>(bl, U, n, *model, (double*)p.ptab, (double*)p.qptab);
-    VB_CUDA(cudaGetLastError());
-  }
   if (want_grad)
-    prune_kernel<true><<<cfg.grid, TILE, cfg.smem, stream>>>(p);
+    prune_kernel<true><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
   else
-    prune_kernel<false><<<cfg.grid, TILE, cfg.smem, stream>>>(p);
+    prune_kernel<false><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
   VB_CUDA(cudaGetLastError());
   {
     dim3 grid((unsigned)U, (unsigned)((2 * n - 2 + 127) / 128));
@@ -450,8 +661,9 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
   }
   g_stats[0] = 3, g_stats[1] = cfg.grid, g_stats[2] = TILE, g_stats[3] = (int64_t)cfg.smem;
   {
-    // algorithmic HBM bytes of prune_kernel: every non-root internal message written once and
-    // read once, tip codes read once per pass, counts, per-site ll out, per-tile gradient partials out.
+    // Algorithmic HBM bytes of prune_kernel: every non-root internal message written once and read
+    // once (32 B per site), tip codes 1 B per tip-site and pass, counts, per-site ll out, per-tile gradient
+    // partials out.  The per-unit step tables are L2-resident across a unit's tiles and not counted.
     const double S = (double)tips->S;
     double bytes = (double)U * S * n * (want_grad ? 2.0 : 1.0) + (double)U * S * 8.0 + (site_ll ? (double)U * S * 8.0 : 0.0);
     if (want_grad) bytes += (double)U * S * (n - 2) * 32.0 * 2.0 + (double)U * cfg.tiles * (2.0 * n - 2) * 8.0;

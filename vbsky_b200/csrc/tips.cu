@@ -77,6 +77,21 @@ __global__ void pack_tips_kernel(const uint8_t* __restrict__ patterns, uint8_t* 
     if (c < n && s < S_pad) dst[(long long)c * S_pad + s] = tile[threadIdx.x][r];
   }
 }
+
+// tip-major ranks [n][S_pad] -> schedule-ordered, tile-major rows [tiles][2(n-1)][kTile]:
+// row 2s / 2s+1 holds the codes of child a / b of step s when that child is a tip.
+__global__ void order_tips_kernel(const uint8_t* __restrict__ tipmajor, const Op* __restrict__ ops, int n,
+                                  long long S_pad, uint8_t* __restrict__ out) {
+  const int rows = 2 * (n - 1);
+  const int tile = blockIdx.x;
+  for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+    const Op op = ops[row >> 1];
+    const int node = (row & 1) ? ((op.x >> 16) & 0xffff) : (op.x & 0xffff);
+    uint8_t v = 4;  // 'N' filler for internal children (never read)
+    if (node < n) v = tipmajor[(long long)node * S_pad + (long long)tile * kTile + threadIdx.x];
+    out[((long long)tile * rows + row) * kTile + threadIdx.x] = v;
+  }
+}
 }  // namespace vbsky
 
 extern "C" int vbsky_encode_tips(const char* seqs, int64_t n, int64_t L, uint8_t* codes) {
@@ -134,27 +149,34 @@ extern "C" int vbsky_compress_patterns(const uint8_t* codes, int64_t L, int64_t 
 
 extern "C" void vbsky_tips_destroy(vbsky_tips* tips) {
   if (!tips) return;
-  cudaFree(tips->d_codes);
+  cudaFree(tips->d_codes_up);
+  cudaFree(tips->d_codes_dn);
   cudaFree(tips->d_counts);
   delete tips;
 }
 
-extern "C" int vbsky_tips_create(int32_t T, int32_t n, int64_t S, const uint8_t* patterns,
+extern "C" int vbsky_tips_create(const vbsky_layout* lay, int64_t S, const uint8_t* patterns,
                                  const double* counts, vbsky_tips** out) {
   VB_CHECK_ARG(out, "out is NULL");
   *out = nullptr;
-  VB_CHECK_ARG(T >= 1 && n >= 2 && S >= 1, "bad shape T=%d n=%d S=%lld", T, n, (long long)S);
+  VB_CHECK_ARG(lay, "layout is NULL");
+  VB_CHECK_ARG(lay->device >= 0, "layout was created without a CUDA device; there is no CPU fallback");
+  const int32_t T = lay->T, n = lay->n;
+  VB_CHECK_ARG(S >= 1, "S must be >= 1 (got %lld)", (long long)S);
   VB_CHECK_ARG(patterns && counts, "NULL argument");
   const int64_t total = (int64_t)T * S * n;
   for (int64_t i = 0; i < total; ++i) VB_CHECK_ARG(patterns[i] <= 15, "pattern code %d is not a 4-bit mask", (int)patterns[i]);
 
   auto* tp = new vbsky_tips();
   tp->T = T, tp->n = n, tp->S = S;
-  tp->S_pad = (S + 255) / 256 * 256;
-  int rc = VBSKY_OK;
-  uint8_t* d_raw = nullptr;
+  tp->S_pad = (S + kTile - 1) / kTile * kTile;
+  tp->tiles = (int32_t)(tp->S_pad / kTile);
+  const size_t rows = 2 * (size_t)(n - 1);
+  const size_t per_tree = rows * tp->S_pad;
+  uint8_t *d_raw = nullptr, *d_tipmajor = nullptr;
   auto fail = [&](int code) {
     cudaFree(d_raw);
+    cudaFree(d_tipmajor);
     vbsky_tips_destroy(tp);
     return code;
   };
@@ -164,22 +186,29 @@ extern "C" int vbsky_tips_create(int32_t T, int32_t n, int64_t S, const uint8_t*
     if (_e != cudaSuccess) return fail(set_error(VBSKY_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e))); \
   } while (0)
   VB_TRY(cudaGetDevice(&tp->device));
-  VB_TRY(cudaMalloc((void**)&tp->d_codes, (size_t)T * n * tp->S_pad));
+  VB_TRY(cudaMalloc((void**)&tp->d_codes_up, (size_t)T * per_tree));
+  VB_TRY(cudaMalloc((void**)&tp->d_codes_dn, (size_t)T * per_tree));
   VB_TRY(cudaMalloc((void**)&tp->d_counts, (size_t)T * tp->S_pad * sizeof(double)));
   VB_TRY(cudaMemset(tp->d_counts, 0, (size_t)T * tp->S_pad * sizeof(double)));
   VB_TRY(cudaMemcpy2D(tp->d_counts, tp->S_pad * sizeof(double), counts, S * sizeof(double), S * sizeof(double), T, cudaMemcpyHostToDevice));
-  // Upload the masks tree by tree (bounded staging buffer) and transpose/remap on the device.
+  // Upload the masks tree by tree (bounded staging buffers); transpose/remap, then gather rows in schedule order.
   VB_TRY(cudaMalloc((void**)&d_raw, (size_t)S * n));
+  VB_TRY(cudaMalloc((void**)&d_tipmajor, (size_t)n * tp->S_pad));
   for (int t = 0; t < T; ++t) {
     VB_TRY(cudaMemcpy(d_raw, patterns + (size_t)t * S * n, (size_t)S * n, cudaMemcpyHostToDevice));
     dim3 grid((unsigned)((tp->S_pad + 31) / 32), (unsigned)((n + 31) / 32), 1), block(32, 8);
-    pack_tips_kernel<<<grid, block>>>(d_raw, tp->d_codes + (size_t)t * n * tp->S_pad, n, S, tp->S_pad);
+    pack_tips_kernel<<<grid, block>>>(d_raw, d_tipmajor, n, S, tp->S_pad);
+    VB_TRY(cudaGetLastError());
+    dim3 g2((unsigned)tp->tiles, (unsigned)std::min<size_t>(rows, 64));
+    order_tips_kernel<<<g2, kTile>>>(d_tipmajor, lay->d_up + (size_t)t * (n - 1), n, tp->S_pad, tp->d_codes_up + (size_t)t * per_tree);
+    VB_TRY(cudaGetLastError());
+    order_tips_kernel<<<g2, kTile>>>(d_tipmajor, lay->d_down + (size_t)t * (n - 1), n, tp->S_pad, tp->d_codes_dn + (size_t)t * per_tree);
     VB_TRY(cudaGetLastError());
   }
   VB_TRY(cudaDeviceSynchronize());
 #undef VB_TRY
   cudaFree(d_raw);
-  (void)rc;
+  cudaFree(d_tipmajor);
   *out = tp;
   return VBSKY_OK;
 }

@@ -54,7 +54,7 @@ class Ensemble:
                 self.T, self.n, _lib.np_ptr(pc, C.c_int32), _lib.np_ptr(cp, C.c_int32),
                 _lib.np_ptr(po, C.c_int32), _lib.np_ptr(st, C.c_double), C.byref(self._layout)))
             _lib.check(_lib.lib.vbsky_tips_create(
-                self.T, self.n, self.S, _lib.np_ptr(patterns, C.c_uint8), _lib.np_ptr(counts, C.c_double),
+                self._layout, self.S, _lib.np_ptr(patterns, C.c_uint8), _lib.np_ptr(counts, C.c_double),
                 C.byref(self._tips)))
         self._ws = None
         info = (C.c_int32 * 8)()
