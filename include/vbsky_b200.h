@@ -122,7 +122,7 @@ void vbsky_tips_destroy(vbsky_tips* tips);
  *     vmap(prune.prune_loglik, (None,None,0,...))(bl, Q, partials, td) * counts   (bdsky.py:331-343)
  * and its custom derivative prune_loglik_jvp (prune.py:134-150, eq. 9).
  *
- *   unit_tree  host [U]            tree index of each unit
+ *   unit_tree  dev  [U]            tree index of each unit
  *   bl         dev  [U][2n-2]      branch length above each node, ALREADY times clock_rate
  *   site_ll    dev  [U][S]         per-pattern log-likelihood (prune_loglik's value); may be NULL
  *   ll         dev  [U]            sum_s counts[s] * site_ll[s]
@@ -140,6 +140,27 @@ int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, 
  * out[1]=persistent CTAs, out[2]=sites per CTA tile, out[3]=dynamic smem bytes per CTA,
  * out[4]=algorithmic HBM bytes of the fused pruning kernel (DESIGN.md formula).               */
 int vbsky_prune_last_stats(int64_t out[8]);
+
+/* CUDA-event timing of the fused pruning kernel alone (used for the roofline figure): after
+ * vbsky_prune_timing(1, NULL, NULL) every prune call of this thread brackets the kernel with an
+ * event pair on its stream; a later call drains them into *ms_sum / *launches (and sets the new
+ * enable state).                                                                               */
+int vbsky_prune_timing(int32_t enable, double* ms_sum, int64_t* launches);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer entry point: what a caller that holds NumPy arrays (the reference's jitted
+ * `step` receives its arguments that way, fasta.py:461-471) binds.  A session owns the device
+ * staging buffers and workspace for up to U_max units.  The call copies unit_tree/bl host ->
+ * device, runs vbsky_prune_value_and_grad, copies ll (and dll_dbl unless NULL) back and
+ * synchronises the stream before returning.  Pinned host memory makes the copies asynchronous
+ * DMA; pageable memory works too.                                                              */
+typedef struct vbsky_session vbsky_session;
+int vbsky_session_create(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U_max,
+                         vbsky_session** out);
+void vbsky_session_destroy(vbsky_session* s);
+int vbsky_prune_value_and_grad_host(vbsky_session* s, int32_t U, const int32_t* unit_tree,
+                                    const double* bl, const vbsky_subst_model* model, double* ll,
+                                    double* dll_dbl, void* stream);
 
 #ifdef __cplusplus
 }

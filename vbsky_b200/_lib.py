@@ -61,6 +61,10 @@ SIGNATURES = {
         [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _vp, _vp, _vp, _vp, C.c_size_t, _vp],
     ),
     "vbsky_prune_last_stats": (C.c_int, [_i64p]),
+    "vbsky_prune_timing": (C.c_int, [C.c_int32, _f64p, _i64p]),
+    "vbsky_session_create": (C.c_int, [_vp, _vp, C.c_int32, C.POINTER(_vp)]),
+    "vbsky_session_destroy": (None, [_vp]),
+    "vbsky_prune_value_and_grad_host": (C.c_int, [_vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _vp, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

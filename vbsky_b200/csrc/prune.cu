@@ -479,20 +479,24 @@ struct TablesParams {
 
 // P(t) = U diag(exp(d t)) Uinv (substitution.py:61-62); optionally Q P(t) = U diag(d exp(d t)) Uinv.
 __device__ __forceinline__ bool expm16(const vbsky_subst_model& m, double t, double* P, double* QP) {
-  double e[4];
+  // Entries are accumulated as delta_ij + sum_k U_ik expm1(d_k t) Uinv_kj: for the short branches of
+  // real data (t ~ 1e-6..1e-3) the off-diagonals of sum_k U_ik exp(d_k t) Uinv_kj are the remainder of
+  // O(1) terms cancelling, i.e. carry ~1e-16/t relative rounding noise (as the reference's own
+  // expm_action does); the expm1 form is exact to ~1 ulp.
+  double e1[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) e[k] = exp(t * m.d[k]);
+  for (int k = 0; k < 4; ++k) e1[k] = expm1(t * m.d[k]);
   bool small = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      double s = 0.0, q = 0.0;
+      double s = (i == j) ? 1.0 : 0.0, q = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const double w = m.P[i * 4 + k] * (e[k] * m.Pinv[k * 4 + j]);
-        s += w;
-        q += m.d[k] * w;
+        const double uu = m.P[i * 4 + k] * m.Pinv[k * 4 + j];
+        s += uu * e1[k];
+        q += (m.d[k] * uu) * (e1[k] + 1.0);
       }
       P[i * 4 + j] = s;
       if (QP) QP[i * 4 + j] = q;
@@ -557,6 +561,14 @@ struct PruneConfig {
 };
 
 static thread_local int64_t g_stats[8] = {0};
+
+// Optional CUDA-event timing of prune_kernel alone (bench.py's roofline leg): when enabled, every call
+// brackets the kernel with an event pair on the launch stream; vbsky_prune_timing() drains them.
+struct TimingState {
+  bool enabled = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+static thread_local TimingState g_timing;
 
 static int prune_config(const vbsky_layout* lay, const vbsky_tips* tips, int U, bool want_grad, PruneConfig* cfg) {
   const int n = lay->n;
@@ -649,11 +661,21 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
   for (int i = 0; i < 4; ++i) p.pi[i] = model->pi[i];
   p.n = n, p.U = U, p.tiles = cfg.tiles, p.depth = cfg.depth;
   p.S = tips->S, p.S_pad = tips->S_pad;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_timing.enabled) {
+    VB_CUDA(cudaEventCreate(&ev0));
+    VB_CUDA(cudaEventCreate(&ev1));
+    VB_CUDA(cudaEventRecord(ev0, stream));
+  }
   if (want_grad)
     prune_kernel<true><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
   else
     prune_kernel<false><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
   VB_CUDA(cudaGetLastError());
+  if (g_timing.enabled) {
+    VB_CUDA(cudaEventRecord(ev1, stream));
+    g_timing.pending.push_back({ev0, ev1});
+  }
   {
     dim3 grid((unsigned)U, (unsigned)((2 * n - 2 + 127) / 128));
     finalize_kernel<<<grid, 128, 0, stream>>>(p.ll_part, p.g_part, unit_tree, lay->d_down_nodes, U, n, cfg.tiles, ll, dll_dbl);
@@ -675,5 +697,83 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
 extern "C" int vbsky_prune_last_stats(int64_t out[8]) {
   VB_CHECK_ARG(out, "NULL argument");
   for (int i = 0; i < 8; ++i) out[i] = g_stats[i];
+  return VBSKY_OK;
+}
+
+extern "C" int vbsky_prune_timing(int32_t enable, double* ms_sum, int64_t* launches) {
+  // Drain: waits for the recorded events, returns the summed prune_kernel time and launch count.
+  double tot = 0.0;
+  int64_t cnt = 0;
+  for (auto& pr : g_timing.pending) {
+    float ms = 0.f;
+    VB_CUDA(cudaEventSynchronize(pr.second));
+    VB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    tot += ms, ++cnt;
+    cudaEventDestroy(pr.first), cudaEventDestroy(pr.second);
+  }
+  g_timing.pending.clear();
+  g_timing.enabled = enable != 0;
+  if (ms_sum) *ms_sum = tot;
+  if (launches) *launches = cnt;
+  return VBSKY_OK;
+}
+
+// ---------------------------------------------------------------------------- host-buffer entry point
+struct vbsky_session {
+  const vbsky_layout* lay = nullptr;
+  const vbsky_tips* tips = nullptr;
+  int32_t U_max = 0;
+  int32_t* d_unit_tree = nullptr;
+  double *d_bl = nullptr, *d_ll = nullptr, *d_dll = nullptr;
+  void* d_ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+extern "C" void vbsky_session_destroy(vbsky_session* s) {
+  if (!s) return;
+  cudaFree(s->d_unit_tree), cudaFree(s->d_bl), cudaFree(s->d_ll), cudaFree(s->d_dll), cudaFree(s->d_ws);
+  delete s;
+}
+
+extern "C" int vbsky_session_create(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U_max, vbsky_session** out) {
+  VB_CHECK_ARG(lay && tips && out, "NULL argument");
+  VB_CHECK_ARG(U_max >= 1, "U_max must be >= 1");
+  *out = nullptr;
+  auto* s = new vbsky_session();
+  s->lay = lay, s->tips = tips, s->U_max = U_max;
+  const size_t nb = 2 * (size_t)lay->n - 2;
+  s->ws_bytes = vbsky_prune_workspace_bytes(lay, tips, U_max, 1);
+  if (s->ws_bytes == 0) {
+    delete s;
+    return VBSKY_EINVAL;
+  }
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_unit_tree, U_max * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_bl, U_max * nb * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ll, U_max * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_dll, U_max * nb * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_ws, s->ws_bytes);
+  if (e != cudaSuccess) {
+    vbsky_session_destroy(s);
+    return set_error(VBSKY_ENOMEM, "session allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return VBSKY_OK;
+}
+
+extern "C" int vbsky_prune_value_and_grad_host(vbsky_session* s, int32_t U, const int32_t* unit_tree, const double* bl,
+                                               const vbsky_subst_model* model, double* ll, double* dll_dbl, void* stream_) {
+  VB_CHECK_ARG(s && unit_tree && bl && model && ll, "NULL argument");
+  VB_CHECK_ARG(U >= 1 && U <= s->U_max, "U=%d outside the session's capacity %d", U, s->U_max);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t nb = 2 * (size_t)s->lay->n - 2;
+  VB_CUDA(cudaMemcpyAsync(s->d_unit_tree, unit_tree, U * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  VB_CUDA(cudaMemcpyAsync(s->d_bl, bl, U * nb * sizeof(double), cudaMemcpyHostToDevice, stream));
+  int rc = vbsky_prune_value_and_grad(s->lay, s->tips, U, s->d_unit_tree, s->d_bl, model, nullptr, s->d_ll,
+                                      dll_dbl ? s->d_dll : nullptr, s->d_ws, s->ws_bytes, stream_);
+  if (rc != VBSKY_OK) return rc;
+  VB_CUDA(cudaMemcpyAsync(ll, s->d_ll, U * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (dll_dbl) VB_CUDA(cudaMemcpyAsync(dll_dbl, s->d_dll, U * nb * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  VB_CUDA(cudaStreamSynchronize(stream));
   return VBSKY_OK;
 }

@@ -62,6 +62,9 @@ class Ensemble:
         self.depth_up, self.depth_down, self.max_levels = info[2], info[3], info[4]
 
     def close(self):
+        if getattr(self, "_session", None):
+            _lib.lib.vbsky_session_destroy(self._session)
+            self._session = None
         if getattr(self, "_layout", None):
             _lib.lib.vbsky_layout_destroy(self._layout)
             self._layout = None
@@ -117,6 +120,40 @@ class Ensemble:
                 self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model),
                 _ptr(site), _ptr(ll), _ptr(dll), _ptr(ws), ws.numel(), C.c_void_p(stream)))
         return ll, dll, site
+
+    def prune_host(self, bl: np.ndarray, unit_tree: np.ndarray, ll_out: Optional[np.ndarray] = None,
+                   dll_out: Optional[np.ndarray] = None, want_grad: bool = True):
+        """Host-buffer call (vbsky_prune_value_and_grad_host): bl [U, 2n-2] float64 and unit_tree [U]
+        int32 NumPy arrays (pinned memory recommended) -> (ll [U], dll_dbl [U, 2n-2]) NumPy arrays.
+        Copies in, computes, copies out and synchronises."""
+        U = bl.shape[0]
+        assert bl.dtype == np.float64 and bl.flags.c_contiguous and bl.shape == (U, 2 * self.n - 2)
+        assert unit_tree.dtype == np.int32 and unit_tree.shape == (U,)
+        with torch.cuda.device(self.device):
+            if getattr(self, "_session", None) is None or self._session_cap < U:
+                if getattr(self, "_session", None) is not None:
+                    _lib.lib.vbsky_session_destroy(self._session)
+                self._session = C.c_void_p()
+                _lib.check(_lib.lib.vbsky_session_create(self._layout, self._tips, U, C.byref(self._session)))
+                self._session_cap = U
+            ll = np.empty(U) if ll_out is None else ll_out
+            dll = None
+            if want_grad:
+                dll = np.empty((U, 2 * self.n - 2)) if dll_out is None else dll_out
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib.vbsky_prune_value_and_grad_host(
+                self._session, U, unit_tree.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p),
+                C.byref(self._model), ll.ctypes.data_as(C.c_void_p),
+                None if dll is None else dll.ctypes.data_as(C.c_void_p), C.c_void_p(stream)))
+        return ll, dll
+
+    @staticmethod
+    def kernel_timing(enable: bool):
+        """Enable/disable CUDA-event timing of the fused pruning kernel; returns (ms_sum, launches)
+        accumulated since the previous call."""
+        ms, cnt = C.c_double(0.0), C.c_int64(0)
+        _lib.check(_lib.lib.vbsky_prune_timing(int(enable), C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     @staticmethod
     def last_stats():
