@@ -65,6 +65,7 @@ def sims(kind="constant", ntaxa=12, nsites=300):
     n = td.n
     import torch
 
+    torch.set_default_dtype(torch.float64)
     m = 5
     params = dict(
         proportions=torch.tensor(rng.uniform(0.2, 0.8, n - 2)), root_proportion=torch.tensor([0.55]),
