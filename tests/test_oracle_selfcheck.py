@@ -9,8 +9,10 @@ import numpy as np
 import pytest
 import torch
 
-import oracle.bdsky as obdsky
-import oracle.cref as cref
+torch.set_default_dtype(torch.float64)
+
+import oracle.bdsky as obdsky  # noqa: E402
+import oracle.cref as cref  # noqa: E402
 import oracle.prune as oprune
 import oracle.substitution as osub
 import oracle.tree_data as otd
