@@ -141,6 +141,82 @@ int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, 
  * out[4]=algorithmic HBM bytes of the fused pruning kernel (DESIGN.md formula).               */
 int vbsky_prune_last_stats(int64_t out[8]);
 
+/* ------------------------------------------------------------------------------------------
+ * Model parameters of bdsky.loglik (bdsky.py:268-345), one row per unit, all device pointers:
+ * the reference's `params` dict after optim.unpack (optim.py:19-32), vmapped over the sample
+ * axis (optim.py:72).  proportions [U][n-2]; root_proportion, origin, origin_start, clock_rate
+ * [U]; R, delta, s, rho [U][m].                                                              */
+typedef struct vbsky_params {
+  const double* proportions;
+  const double* root_proportion;
+  const double* origin;
+  const double* origin_start;
+  const double* clock_rate;
+  const double* R;
+  const double* delta;
+  const double* s;
+  const double* rho;
+} vbsky_params;
+
+/* Gradients w.r.t. the same fields (origin_start shares origin's gradient; both enter as a sum).
+ * R/delta/s/rho may be NULL when only the height chain is differentiated.                    */
+typedef struct vbsky_param_grads {
+  double* proportions;
+  double* root_proportion;
+  double* origin;
+  double* clock_rate;
+  double* R;
+  double* delta;
+  double* s;
+  double* rho;
+} vbsky_param_grads;
+
+/* TreeData.height_transform (tree_data.py:287-367) and the glue of bdsky.loglik
+ * (bdsky.py:292-322) for all units: heights [U][2n-1]; bl_scaled [U][2n-2] = (h[parent]-h) *
+ * clock_rate; optional xs [U][2n-1] = tm - heights, times [U][m+1] = linspace(0, tm, m+1),
+ * lam/psi/mu [U][m] (_bdsky_transform, bdsky.py:219-227) with tm = origin + origin_start.
+ * Pass times == NULL (and m == 0) to skip the skyline outputs.                                */
+int vbsky_heights_forward(const vbsky_layout* lay, int32_t U, const int32_t* unit_tree, int32_t m,
+                          const vbsky_params* in, double* heights, double* bl_scaled, double* xs,
+                          double* times, double* lam, double* psi, double* mu, void* stream);
+
+/* Adjoint of vbsky_heights_forward: given d/d(bl_scaled), d/d(xs), d/d(times), d/d(lam, psi, mu)
+ * (any may be NULL = 0) accumulate the gradient w.r.t. proportions, root_proportion, origin,
+ * clock_rate and (if out->R != NULL) R, delta, s.  ws: >= U*(2n-1)*8 bytes.                   */
+int vbsky_heights_backward(const vbsky_layout* lay, int32_t U, const int32_t* unit_tree, int32_t m,
+                           const vbsky_params* in, const double* heights,
+                           const double* d_bl_scaled, const double* d_xs, const double* d_times,
+                           const double* d_lam, const double* d_psi, const double* d_mu,
+                           vbsky_param_grads* out, void* ws, size_t ws_bytes, void* stream);
+
+/* _tree_loglik (bdsky.py:18-216): birth-death-skyline log-density of Stadler et al. (2013),
+ * Thm 1, for U units at once, and its gradient (the reference obtains it by JAX autodiff).
+ * lam, psi, mu, rho [U][m]; xs [U][2n-1] (forward node times, tips first); times [U][m+1].
+ * Out-of-range interval indices clamp (jnp.take clip semantics).  Outputs: lp [U];
+ * if dlam != NULL also dlam, dpsi, dmu, drho [U][m], dxs [U][2n-1], dtimes [U][m+1].           */
+size_t vbsky_bdsky_workspace_bytes(int32_t U, int32_t n);
+int vbsky_bdsky_value_and_grad(int32_t U, int32_t n, int32_t m, const double* lam,
+                               const double* psi, const double* mu, const double* rho,
+                               const double* xs, const double* times,
+                               int32_t condition_on_survival, double* lp, double* dlam,
+                               double* dpsi, double* dmu, double* drho, double* dxs,
+                               double* dtimes, void* ws, size_t ws_bytes, void* stream);
+
+/* bdsky.loglik (bdsky.py:268-345) without the user prior term c[0]: for every unit
+ *   ll = [flags&1] _tree_loglik(...) + [flags&2] sum_s counts[s] * prune_loglik(...)
+ * and the gradient w.r.t. every field of vbsky_params (grads == NULL => value only).
+ * flags: bit0 tree-prior term (c[1]), bit1 data term (c[2]), bit2 condition_on_survival.
+ * ll_tree / ll_data [U] may be NULL.  Six kernel launches, no host synchronisation.            */
+#define VBSKY_TERM_TREE 1
+#define VBSKY_TERM_DATA 2
+#define VBSKY_CONDITION_ON_SURVIVAL 4
+size_t vbsky_loglik_workspace_bytes(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, int32_t m);
+int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                const int32_t* unit_tree, int32_t m, const vbsky_params* in,
+                                const vbsky_subst_model* model, int32_t flags, double* ll,
+                                double* ll_tree, double* ll_data, vbsky_param_grads* grads,
+                                void* ws, size_t ws_bytes, void* stream);
+
 /* CUDA-event timing of the fused pruning kernel alone (used for the roofline figure): after
  * vbsky_prune_timing(1, NULL, NULL) every prune call of this thread brackets the kernel with an
  * event pair on its stream; a later call drains them into *ms_sum / *launches (and sets the new

@@ -33,6 +33,18 @@ class SubstModel(C.Structure):
     _fields_ = [("pi", C.c_double * 4), ("P", C.c_double * 16), ("d", C.c_double * 4), ("Pinv", C.c_double * 16)]
 
 
+class Params(C.Structure):
+    """vbsky_params: device pointers, one row per unit."""
+
+    _fields_ = [(k, C.c_void_p) for k in ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho")]
+
+
+class ParamGrads(C.Structure):
+    """vbsky_param_grads."""
+
+    _fields_ = [(k, C.c_void_p) for k in ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho")]
+
+
 _vp = C.c_void_p
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -62,6 +74,15 @@ SIGNATURES = {
     ),
     "vbsky_prune_last_stats": (C.c_int, [_i64p]),
     "vbsky_prune_timing": (C.c_int, [C.c_int32, _f64p, _i64p]),
+    "vbsky_heights_forward": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vbsky_heights_backward": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         C.POINTER(ParamGrads), _vp, C.c_size_t, _vp]),
+    "vbsky_bdsky_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "vbsky_bdsky_value_and_grad": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int32,
+                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vbsky_loglik_workspace_bytes": (C.c_size_t, [_vp, _vp, C.c_int32, C.c_int32]),
+    "vbsky_loglik_value_and_grad": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), C.POINTER(SubstModel),
+                                              C.c_int32, _vp, _vp, _vp, C.POINTER(ParamGrads), _vp, C.c_size_t, _vp]),
     "vbsky_session_create": (C.c_int, [_vp, _vp, C.c_int32, C.POINTER(_vp)]),
     "vbsky_session_destroy": (None, [_vp]),
     "vbsky_prune_value_and_grad_host": (C.c_int, [_vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _vp, _vp, _vp]),

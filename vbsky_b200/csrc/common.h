@@ -53,6 +53,7 @@ struct vbsky_layout {
   std::vector<int32_t> h_msg_rows;            // [T][n-2] scratch rows of internal children in down-pass consumption order
   std::vector<int32_t> h_msg_start;           // [T][nchunks+1] prefix of h_msg_rows per chunk of kChunkSteps down steps
   std::vector<int32_t> h_child_parent;        // [T][N]
+  std::vector<int32_t> h_parent_child;        // [T][N][2]
   std::vector<int32_t> h_siblings;            // [T][N]
   std::vector<double> h_lst;                  // [T][N]
   std::vector<double> h_sample_times;         // [T][n]
@@ -66,6 +67,7 @@ struct vbsky_layout {
   int32_t* d_msg_rows = nullptr;
   int32_t* d_msg_start = nullptr;
   int32_t* d_child_parent = nullptr;
+  int32_t* d_parent_child = nullptr;
   double* d_lst = nullptr;
   double* d_sample_times = nullptr;
   double* d_max_sample_time = nullptr;

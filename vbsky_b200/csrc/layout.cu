@@ -187,6 +187,7 @@ extern "C" void vbsky_layout_destroy(vbsky_layout* lay) {
   cudaFree(lay->d_msg_rows);
   cudaFree(lay->d_msg_start);
   cudaFree(lay->d_child_parent);
+  cudaFree(lay->d_parent_child);
   cudaFree(lay->d_lst);
   cudaFree(lay->d_sample_times);
   cudaFree(lay->d_max_sample_time);
@@ -214,6 +215,7 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   lay->h_msg_rows.assign((size_t)T * std::max(n - 2, 1), 0);
   lay->h_msg_start.assign((size_t)T * (nchunks + 1), 0);
   lay->h_child_parent.assign(child_parent, child_parent + (size_t)T * N);
+  lay->h_parent_child.assign(parent_child, parent_child + (size_t)T * N * 2);
   lay->h_siblings.assign((size_t)T * N, -1);
   lay->h_lst.assign((size_t)T * N, 0.0);
   lay->h_sample_times.assign(sample_times, sample_times + (size_t)T * n);
@@ -315,6 +317,7 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   VB_UP(d_msg_rows, h_msg_rows)
   VB_UP(d_msg_start, h_msg_start)
   VB_UP(d_child_parent, h_child_parent)
+  VB_UP(d_parent_child, h_parent_child)
   VB_UP(d_lst, h_lst)
   VB_UP(d_sample_times, h_sample_times)
   VB_UP(d_max_sample_time, h_max_sample_time)
