@@ -32,6 +32,7 @@ WORKLOADS = {
     "tiny": (4, 16, 300, 2, 1.12e-3),
 }
 KAPPA = 2.7
+M_INTERVALS = 50  # skyline intervals (paper/covid.py m=50)
 UNIT = "ELBO+grad evals/s"
 METRIC = "elbo_grad_evals_per_sec"
 
@@ -185,19 +186,37 @@ def main():
     units = [(t, k) for t in range(T) for k in range(K)]
     mine = units[rank::world]
     U = len(mine)
-    bl_host = np.stack([data.heights[t].branch_lengths[k] for (t, k) in mine]) * clock
+    m = M_INTERVALS
+    rng = np.random.default_rng(12345)
+    Rk = rng.lognormal(0.0, 0.5, (K, m))  # one draw of the global skyline parameters per MC sample
+    host = {
+        "proportions": np.stack([data.heights[t].proportions[k] for (t, k) in mine]),
+        "root_proportion": np.array([data.heights[t].root_proportion[k] for (t, k) in mine]),
+        "origin": np.full(U, data.origin),
+        "origin_start": np.array([data.tds[t].sample_times.max() for (t, _) in mine]),
+        "clock_rate": np.full(U, clock),
+        "R": np.stack([Rk[k] for (_, k) in mine]),
+        "delta": np.full((U, m), 36.5), "s": np.full((U, m), 0.02), "rho": np.zeros((U, m)),
+    }
+    host = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in host.items()}
     ut_host = np.array([t for (t, _) in mine], dtype=np.int32)
-    bl = torch.as_tensor(bl_host, device=dev)
+    params = {k: torch.as_tensor(v, device=dev) for k, v in host.items()}
     ut = torch.as_tensor(ut_host, device=dev)
-    elbo = torch.zeros(1, dtype=torch.float64, device=dev)
+    grads = {k: torch.empty_like(params[k]) for k in Ensemble.GRAD_KEYS}
+    out = {k: torch.empty(U, dtype=torch.float64, device=dev) for k in ("ll", "tree", "data")}
+    GLOBAL = ("origin", "clock_rate", "R", "delta", "s", "rho")
+    red = torch.zeros(1 + 2 + 4 * m, dtype=torch.float64, device=dev)
 
     def step():
-        ll, dll, _ = ens.prune(bl, ut, want_grad=True)
-        # ELBO data term: mean over samples of the per-tree log-likelihoods, summed over trees
-        elbo.copy_(ll.sum().reshape(1) / K)
+        # ELBO likelihood part: mean over the K samples of loglik, summed over trees (optim.py:72-75, fasta.py:456-487
+        # batched over the ensemble), and its gradient; gradients of the per-tree (local) parameters stay on their owner.
+        ens.loglik_device(params, ut, m, flags=7, grads=grads, out=out)
+        red[0] = out["ll"].sum() / K
+        red[1] = grads["origin"].sum() / K
+        red[2] = grads["clock_rate"].sum() / K
+        torch.sum(torch.stack([grads["R"], grads["delta"], grads["s"], grads["rho"]], 0), dim=1, out=red[3:].view(4, m))
         if world > 1:
-            dist.all_reduce(elbo)
-        return ll, dll
+            dist.all_reduce(red)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -212,7 +231,7 @@ def main():
     torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        ll, dll = step()
+        step()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -225,18 +244,20 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_step = tms.item() / args.steps
     stats = ens.last_stats()
+    ll_dev = out["ll"].cpu().numpy()
 
-    # ---- end-to-end through the host-buffer C ABI: pinned inputs -> H2D -> kernels -> D2H of ll + gradient
-    bl_pin = torch.as_tensor(bl_host).pin_memory()
-    ut_pin = torch.as_tensor(ut_host).pin_memory()
-    ll_pin = torch.empty(U, dtype=torch.float64).pin_memory()
-    dll_pin = torch.empty(U, 2 * n - 2, dtype=torch.float64).pin_memory()
+    # ---- end-to-end through the host-buffer C ABI: pinned params -> H2D -> 7 kernels -> D2H of ll + every gradient
+    pin = lambda a: torch.as_tensor(a).pin_memory().numpy()
+    hp = {k: pin(v) for k, v in host.items()}
+    hut = pin(ut_host)
+    hg = {k: pin(np.empty_like(host[k])) for k in Ensemble.GRAD_KEYS}
+    ho = {k: pin(np.empty(U)) for k in ("ll", "tree", "data")}
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step():
-        ens.prune_host(bl_pin.numpy(), ut_pin.numpy(), ll_out=ll_pin.numpy(), dll_out=dll_pin.numpy())
+        ens.loglik_host(hp, hut, m, flags=7, grads=hg, out=ho)
         if world > 1:
-            v = torch.tensor([float(ll_pin.sum()) / K], dtype=torch.float64, device=dev)
+            v = torch.tensor([float(ho["ll"].sum()) / K], dtype=torch.float64, device=dev)
             dist.all_reduce(v)
 
     e2e_step()
@@ -250,9 +271,10 @@ def main():
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    assert np.allclose(ll_pin.numpy(), ll.cpu().numpy(), rtol=1e-12), "host-buffer path disagrees with the device path"
-    h2d = bl_host.nbytes + ut_host.nbytes
-    d2h = U * 8 + U * (2 * n - 2) * 8
+    assert np.allclose(ho["ll"], ll_dev, rtol=1e-12), "host-buffer path disagrees with the device path"
+    assert np.isfinite(ll_dev).all() and all(np.isfinite(v).all() for v in hg.values()), "non-finite ELBO / gradient"
+    h2d = sum(v.nbytes for v in host.values()) + ut_host.nbytes
+    d2h = 3 * U * 8 + sum(v.nbytes for v in hg.values())
 
     if rank != 0:
         if world > 1:
@@ -272,14 +294,15 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": f"{args.workload}: {T} trees x {n} tips x {S} site patterns, K={K} height samples/tree, HKY({KAPPA}), "
-                        f"value+grad of the data log-likelihood for all {T * K} (tree,sample) units",
-            "sharding": f"{T * K} units round-robin over {world} rank(s); one all-reduce of the ELBO value per step",
+                        f"m={M_INTERVALS} skyline intervals; one step = value+grad of bdsky.loglik (BDSKY tree prior + data log-likelihood) "
+                        f"w.r.t. all parameters for all {T * K} (tree,sample) units",
+            "sharding": f"{T * K} units round-robin over {world} rank(s); one all-reduce of [ELBO, d/d global params] ({1 + 2 + 4 * M_INTERVALS} doubles) per step",
             "l2": "working set per step (message scratch + step tables, > 500 MB) exceeds the 126 MB L2; no explicit flush",
             "reduced": bool(args.trees),
         },
         "e2e": {"value": 1e3 / e2e_ms.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "note": "vbsky_prune_value_and_grad_host: pinned host branch lengths in, ll + dll/dbl out, per step; tip codes resident (uploaded once, as prep_data is one-off in the reference)"},
-        "gpu_launches": int(stats["launches"] * args.steps),
+                "note": "vbsky_loglik_value_and_grad_host: pinned host parameters in, ll + all gradients out, per step; tip codes resident (uploaded once, as prep_data is one-off in the reference)"},
+        "gpu_launches": int(7 * args.steps),
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "kernel": "prune_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -293,7 +316,7 @@ def main():
         sec, threads, _ = cpu_reference_sample(data, sample_units, K, clock)
         v = 1.0 / (sec * len(units) / len(sample_units))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{len(sample_units)} of {len(units)} (tree,sample) units, C/OpenMP restatement of prune.py, {sec:.1f} s, scaled"}
+                                "sample": f"{len(sample_units)} of {len(units)} (tree,sample) units, C/OpenMP restatement of prune.py (data term + d/dbl; the O(n+m) tree prior is not included), {sec:.1f} s, scaled"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -232,11 +232,19 @@ int vbsky_prune_timing(int32_t enable, double* ms_sum, int64_t* launches);
  * DMA; pageable memory works too.                                                              */
 typedef struct vbsky_session vbsky_session;
 int vbsky_session_create(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U_max,
-                         vbsky_session** out);
+                         int32_t m_max, vbsky_session** out);
 void vbsky_session_destroy(vbsky_session* s);
+/* vbsky_prune_value_and_grad with host buffers (unit_tree, bl in; ll, dll_dbl out). */
 int vbsky_prune_value_and_grad_host(vbsky_session* s, int32_t U, const int32_t* unit_tree,
                                     const double* bl, const vbsky_subst_model* model, double* ll,
                                     double* dll_dbl, void* stream);
+/* vbsky_loglik_value_and_grad with host buffers: every pointer in `in`, `grads`, ll, ll_tree,
+ * ll_data and unit_tree is HOST memory here.                                                  */
+int vbsky_loglik_value_and_grad_host(vbsky_session* s, int32_t U, const int32_t* unit_tree,
+                                     int32_t m, const vbsky_params* in,
+                                     const vbsky_subst_model* model, int32_t flags, double* ll,
+                                     double* ll_tree, double* ll_data, vbsky_param_grads* grads,
+                                     void* stream);
 
 #ifdef __cplusplus
 }

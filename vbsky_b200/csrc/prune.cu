@@ -718,62 +718,3 @@ extern "C" int vbsky_prune_timing(int32_t enable, double* ms_sum, int64_t* launc
   return VBSKY_OK;
 }
 
-// ---------------------------------------------------------------------------- host-buffer entry point
-struct vbsky_session {
-  const vbsky_layout* lay = nullptr;
-  const vbsky_tips* tips = nullptr;
-  int32_t U_max = 0;
-  int32_t* d_unit_tree = nullptr;
-  double *d_bl = nullptr, *d_ll = nullptr, *d_dll = nullptr;
-  void* d_ws = nullptr;
-  size_t ws_bytes = 0;
-};
-
-extern "C" void vbsky_session_destroy(vbsky_session* s) {
-  if (!s) return;
-  cudaFree(s->d_unit_tree), cudaFree(s->d_bl), cudaFree(s->d_ll), cudaFree(s->d_dll), cudaFree(s->d_ws);
-  delete s;
-}
-
-extern "C" int vbsky_session_create(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U_max, vbsky_session** out) {
-  VB_CHECK_ARG(lay && tips && out, "NULL argument");
-  VB_CHECK_ARG(U_max >= 1, "U_max must be >= 1");
-  *out = nullptr;
-  auto* s = new vbsky_session();
-  s->lay = lay, s->tips = tips, s->U_max = U_max;
-  const size_t nb = 2 * (size_t)lay->n - 2;
-  s->ws_bytes = vbsky_prune_workspace_bytes(lay, tips, U_max, 1);
-  if (s->ws_bytes == 0) {
-    delete s;
-    return VBSKY_EINVAL;
-  }
-  cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_unit_tree, U_max * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_bl, U_max * nb * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ll, U_max * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_dll, U_max * nb * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&s->d_ws, s->ws_bytes);
-  if (e != cudaSuccess) {
-    vbsky_session_destroy(s);
-    return set_error(VBSKY_ENOMEM, "session allocation failed: %s", cudaGetErrorString(e));
-  }
-  *out = s;
-  return VBSKY_OK;
-}
-
-extern "C" int vbsky_prune_value_and_grad_host(vbsky_session* s, int32_t U, const int32_t* unit_tree, const double* bl,
-                                               const vbsky_subst_model* model, double* ll, double* dll_dbl, void* stream_) {
-  VB_CHECK_ARG(s && unit_tree && bl && model && ll, "NULL argument");
-  VB_CHECK_ARG(U >= 1 && U <= s->U_max, "U=%d outside the session's capacity %d", U, s->U_max);
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const size_t nb = 2 * (size_t)s->lay->n - 2;
-  VB_CUDA(cudaMemcpyAsync(s->d_unit_tree, unit_tree, U * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-  VB_CUDA(cudaMemcpyAsync(s->d_bl, bl, U * nb * sizeof(double), cudaMemcpyHostToDevice, stream));
-  int rc = vbsky_prune_value_and_grad(s->lay, s->tips, U, s->d_unit_tree, s->d_bl, model, nullptr, s->d_ll,
-                                      dll_dbl ? s->d_dll : nullptr, s->d_ws, s->ws_bytes, stream_);
-  if (rc != VBSKY_OK) return rc;
-  VB_CUDA(cudaMemcpyAsync(ll, s->d_ll, U * sizeof(double), cudaMemcpyDeviceToHost, stream));
-  if (dll_dbl) VB_CUDA(cudaMemcpyAsync(dll_dbl, s->d_dll, U * nb * sizeof(double), cudaMemcpyDeviceToHost, stream));
-  VB_CUDA(cudaStreamSynchronize(stream));
-  return VBSKY_OK;
-}

@@ -130,12 +130,7 @@ class Ensemble:
         assert bl.dtype == np.float64 and bl.flags.c_contiguous and bl.shape == (U, 2 * self.n - 2)
         assert unit_tree.dtype == np.int32 and unit_tree.shape == (U,)
         with torch.cuda.device(self.device):
-            if getattr(self, "_session", None) is None or self._session_cap < U:
-                if getattr(self, "_session", None) is not None:
-                    _lib.lib.vbsky_session_destroy(self._session)
-                self._session = C.c_void_p()
-                _lib.check(_lib.lib.vbsky_session_create(self._layout, self._tips, U, C.byref(self._session)))
-                self._session_cap = U
+            self._ensure_session(U, 0)
             ll = np.empty(U) if ll_out is None else ll_out
             dll = None
             if want_grad:
@@ -146,6 +141,78 @@ class Ensemble:
                 C.byref(self._model), ll.ctypes.data_as(C.c_void_p),
                 None if dll is None else dll.ctypes.data_as(C.c_void_p), C.c_void_p(stream)))
         return ll, dll
+
+    def _ensure_session(self, U: int, m: int):
+        cap = getattr(self, "_session_cap", (0, -1))
+        if getattr(self, "_session", None) is None or cap[0] < U or cap[1] < m:
+            if getattr(self, "_session", None) is not None:
+                _lib.lib.vbsky_session_destroy(self._session)
+            self._session = C.c_void_p()
+            cap = (max(U, cap[0]), max(m, cap[1]))
+            _lib.check(_lib.lib.vbsky_session_create(self._layout, self._tips, cap[0], cap[1], C.byref(self._session)))
+            self._session_cap = cap
+
+    GRAD_KEYS = ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho")
+    PARAM_KEYS = ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho")
+
+    def loglik_device(self, params: dict, unit_tree: torch.Tensor, m: int, flags: int = 7, grads: Optional[dict] = None,
+                      out: Optional[dict] = None):
+        """Raw device call of vbsky_loglik_value_and_grad (no autograd): ``params`` / ``grads`` map the
+        vbsky_params / vbsky_param_grads field names to contiguous CUDA fp64 tensors ([U, ...]); ``out``
+        may provide preallocated 'll', 'tree', 'data' [U] tensors.  Returns ``out``."""
+        U = unit_tree.shape[0]
+        cin = _lib.Params()
+        for k in self.PARAM_KEYS:
+            v = params.get(k)
+            setattr(cin, k, 0 if v is None or v.numel() == 0 else v.data_ptr())
+        cg = None
+        if grads is not None:
+            cg = _lib.ParamGrads()
+            for k in self.GRAD_KEYS:
+                v = grads.get(k)
+                setattr(cg, k, 0 if v is None or v.numel() == 0 else v.data_ptr())
+        out = out if out is not None else {}
+        for k in ("ll", "tree", "data"):
+            if k not in out:
+                out[k] = torch.empty(U, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            need = _lib.lib.vbsky_loglik_workspace_bytes(self._layout, self._tips, U, m)
+            if need == 0:
+                raise _lib.VbskyError(-1, _lib.last_error())
+            ws = self._workspace(need)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib.vbsky_loglik_value_and_grad(
+                self._layout, self._tips, U, _ptr(unit_tree), m, C.byref(cin), C.byref(self._model), flags,
+                _ptr(out["ll"]), _ptr(out["tree"]), _ptr(out["data"]), None if cg is None else C.byref(cg),
+                _ptr(ws), ws.numel(), C.c_void_p(stream)))
+        return out
+
+    def loglik_host(self, params: dict, unit_tree: np.ndarray, m: int, flags: int = 7, grads: Optional[dict] = None,
+                    out: Optional[dict] = None):
+        """vbsky_loglik_value_and_grad_host: same as ``loglik_device`` with NumPy (ideally pinned) buffers;
+        copies in, computes, copies out, synchronises."""
+        U = unit_tree.shape[0]
+        hp = lambda a: 0 if a is None or a.size == 0 else a.ctypes.data
+        cin = _lib.Params()
+        for k in self.PARAM_KEYS:
+            setattr(cin, k, hp(params.get(k)))
+        cg = None
+        if grads is not None:
+            cg = _lib.ParamGrads()
+            for k in self.GRAD_KEYS:
+                setattr(cg, k, hp(grads.get(k)))
+        out = out if out is not None else {}
+        for k in ("ll", "tree", "data"):
+            if k not in out:
+                out[k] = np.empty(U)
+        with torch.cuda.device(self.device):
+            self._ensure_session(U, m)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib.vbsky_loglik_value_and_grad_host(
+                self._session, U, unit_tree.ctypes.data_as(C.c_void_p), m, C.byref(cin), C.byref(self._model), flags,
+                out["ll"].ctypes.data_as(C.c_void_p), out["tree"].ctypes.data_as(C.c_void_p),
+                out["data"].ctypes.data_as(C.c_void_p), None if cg is None else C.byref(cg), C.c_void_p(stream)))
+        return out
 
     @staticmethod
     def kernel_timing(enable: bool):
