@@ -39,7 +39,7 @@ struct Op {
 };
 
 // Geometry shared by the host-side layout builder and the pruning kernel.
-constexpr int kTile = 128;        // site patterns per CTA tile (= consumer threads per CTA)
+constexpr int kTile = 256;        // site patterns per CTA tile (two per consumer thread)
 constexpr int kChunkSteps = 4;    // schedule steps delivered per ring stage
 
 }  // namespace vbsky

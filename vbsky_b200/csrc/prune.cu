@@ -5,7 +5,8 @@
 //
 // Design (DESIGN.md "Pruning kernel"):
 //   * persistent, warp-specialised CTAs.  A work item is (unit, tile of kTile site patterns); four
-//     consumer warps own one site pattern per thread for the whole tree walk, a fifth (producer)
+//     consumer warps own two adjacent site patterns per thread for the whole tree walk (two
+//     independent dependency chains per thread, 128-bit shared/global accesses), a fifth (producer)
 //     warp streams everything the walk needs into shared-memory rings with cp.async.bulk (the
 //     1-D TMA path) completing on mbarriers: per-step records {op, P(t) matrices}, the tip codes of
 //     the step and -- in the down pass -- the children's messages from the CTA-private scratch.
@@ -17,13 +18,17 @@
 //     shared-memory stack; the up pass streams each internal node's message to scratch once and
 //     the down pass streams it back once.  pre vectors never leave the SM.  Value-only evaluation
 //     touches no scratch at all;
-//   * per-site scale factors are accumulated as mantissa x 2^exponent (one log per site instead
-//     of one per node, prune.py:37), and the gradient uses the scale-free form of eq. (9),
+//   * the gradient uses the scale-free form of eq. (9),
 //       g_c = (w^T Q m_c) / (w^T m_c),  w = pre_parent (.) m_sibling,
 //     which equals prune.py:146-148 whenever the 1e-40 clips are inactive;
-//   * the clips of substitution.py:70 are applied literally only for units in which they can be
-//     active at all (some P(t) entry below 1e-20, i.e. a branch length of ~0); tables_kernel
-//     decides per unit.  Otherwise every clipped quantity is provably >= 1e-40 and <= 1 + few ulp;
+//   * two arithmetic variants, chosen per unit by tables_kernel:
+//       CLIP    (some P(t) entry below 1e-20, i.e. a branch length of ~0, where the clips of
+//               substitution.py:70 can be active): literal arithmetic -- clip to [1e-40, 1], divide by the
+//               sum (prune.py:31-34, 70-74), scale factors accumulated as mantissa x 2^exponent;
+//       no CLIP (every clipped quantity is provably >= 1e-40 and <= 1 + few ulp): the clips are
+//               dropped and every rescaling is by an exact power of two (exponent arithmetic on the
+//               integer pipe instead of an fp64 division), which changes no result beyond rounding;
+//     either way one log per site instead of one per node (prune.py:37);
 //   * branch gradients are reduced over the tile's sites through a transposed shared-memory
 //     staging buffer, written as per-tile partials and summed in a fixed order by finalize_kernel
 //     (bitwise reproducible).
@@ -33,24 +38,31 @@
 
 namespace vbsky {
 
-constexpr int TILE = kTile;
-constexpr int NCW = TILE / 32;        // consumer warps
-constexpr int THREADS = TILE + 32;    // + producer warp
+constexpr int TILE = kTile;           // site patterns per work item
+constexpr int NS = 2;                 // site patterns per consumer thread (adjacent)
+constexpr int CT = TILE / NS;         // consumer threads
+constexpr int NCW = CT / 32;          // consumer warps
+constexpr int THREADS = CT + 32;      // + producer warp
 constexpr int CH = kChunkSteps;       // steps per ring stage
 constexpr int NST = 3;                // step-chunk ring stages
-constexpr int NMS = 4;                // message ring slots
-constexpr int UPREC = 50;             // doubles per up-step record:   op(2) Pa(16) Pb(16) Pp(16)
-constexpr int DNREC = 66;             // doubles per down-step record: op(2) Pa(16) Pb(16) QPa(16) QPb(16)
+constexpr int NMS = 3;                // message ring slots
+constexpr int TIPM = 20;              // doubles of a tip-branch table: columns of P(t) for A,C,G,T and their sum (N)
+constexpr int UPREC = 2 + 2 * TIPM + 16;  // up-step record:   op(2) Ta(20) Tb(20) Pp(16)
+constexpr int DNREC = 2 + 4 * TIPM;       // down-step record: op(2) Ta|Pa(20) Tb|Pb(20) QTa(20) QTb(20)
+constexpr int UP_A = 2, UP_B = 2 + TIPM, UP_P = 2 + 2 * TIPM;
+constexpr int DN_A = 2, DN_B = 2 + TIPM, DN_QA = 2 + 2 * TIPM, DN_QB = 2 + 3 * TIPM;
 constexpr int CODE_ROW = TILE;        // bytes of tip codes per (step, child)
 constexpr int STAGE_BYTES = CH * DNREC * 8 + 2 * CH * CODE_ROW;
 constexpr int STAGE_CODES = CH * DNREC * 8;  // byte offset of the code rows inside a stage
 constexpr int MSG_BYTES = 4 * TILE * 8;
-constexpr int GCH = 16;               // branch gradients staged per reduction round
+constexpr int GCH = 8;                // branch gradients staged per reduction round
 constexpr int GROW = TILE + 1;
 constexpr int OFF_STAGE = 128;
 constexpr int OFF_MSG = OFF_STAGE + ((NST * STAGE_BYTES + 127) / 128) * 128;
 constexpr int OFF_STK = OFF_MSG + NMS * MSG_BYTES;
+static_assert(NS == 2, "the consumer code is written for two sites per thread");
 static_assert(STAGE_BYTES % 16 == 0 && (UPREC * 8) % 16 == 0 && (DNREC * 8) % 16 == 0, "bulk copies need 16-byte granularity");
+static_assert(CT % GCH == 0 && GCH % 2 == 0, "gradient staging geometry");
 
 struct PruneParams {
   const double* uptab;    // [U][n-1][UPREC]
@@ -93,17 +105,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Producer-side wait: the suspend-time hint lets the thread sleep in hardware until the phase completes
+// instead of spinning in the issue slots of the consumer warp that shares its scheduler.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(bar),
+      "r"(parity), "r"(1000000u)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TILE) : "memory"); }
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
 template <bool CLIP>
 __device__ __forceinline__ double clipv(double x) {
   // jnp.clip(ret, 1e-40, 1.0) of substitution.py:70
   return CLIP ? fmin(fmax(x, 1e-40), 1.0) : x;
+}
+
+// 1/x for a positive normal x: hardware seed + two Newton steps (~1 ulp), no range fix-up.
+__device__ __forceinline__ double rcp_pos(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+// Unbiased binary exponent of a positive normal double and multiplication by 2^-e on the integer pipe.
+__device__ __forceinline__ int exponent_of(double x) { return (__double2hiint(x) >> 20) - 1023; }
+__device__ __forceinline__ double scale_pow2(double x, int e) {
+  return __hiloint2double(__double2hiint(x) - (e << 20), __double2loint(x));
 }
 
 __device__ __forceinline__ void lds16(const double* p, double (&M)[16]) {
@@ -115,24 +152,38 @@ __device__ __forceinline__ void lds16(const double* p, double (&M)[16]) {
   }
 }
 
-// Columns of a 4x4 matrix selected by a tip's state set: M e_mask (substitution.py:10-35 partials).
-// rank < 4 is a single column.
-__device__ __forceinline__ void tip_columns(const double* M, int rank, bool all_simple, double (&out)[4]) {
-  if (all_simple) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) out[i] = M[i * 4 + rank];
+// M e_mask for a tip's state set (substitution.py:10-35 partials).  Tip tables hold the columns of the
+// matrix contiguously (T[r*4 + i] = M[i][r]) plus their sum as a fifth column, so ranks 0..4 (A, C, G, T and
+// the fully ambiguous N) are one 32-byte gather; the other ambiguity codes add up their columns.
+__device__ __forceinline__ void tip_columns(const double* T, int rank, double (&out)[4]) {
+  if (rank <= 4) {
+    const double2 a = *reinterpret_cast<const double2*>(T + rank * 4);
+    const double2 b = *reinterpret_cast<const double2*>(T + rank * 4 + 2);
+    out[0] = a.x, out[1] = a.y, out[2] = b.x, out[3] = b.y;
   } else {
     const int mask = kRankToMask[rank];
-    double A[16];
-    lds16(M, A);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double s = 0.0;
+    for (int i = 0; i < 4; ++i) out[i] = 0.0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s += ((mask >> j) & 1) ? A[i * 4 + j] : 0.0;
-      out[i] = s;
-    }
+    for (int j = 0; j < 4; ++j)
+      if ((mask >> j) & 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] += T[j * 4 + i];
+      }
   }
+}
+
+// rows [4][TILE] of doubles: this thread's two adjacent sites of row i
+__device__ __forceinline__ void load_rows(const double* base, double (&x)[NS][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double2 v = *reinterpret_cast<const double2*>(base + i * TILE);
+    x[0][i] = v.x, x[1][i] = v.y;
+  }
+}
+__device__ __forceinline__ void store_rows(double* base, const double (&x)[NS][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<double2*>(base + i * TILE) = make_double2(x[0][i], x[1][i]);
 }
 
 struct RingState {
@@ -153,6 +204,23 @@ __device__ __forceinline__ uint32_t bar_full_m(uint32_t base, uint32_t s) { retu
 __device__ __forceinline__ uint32_t bar_empty_m(uint32_t base, uint32_t s) { return base + 8 * (2 * NST + NMS + s); }
 __device__ __forceinline__ uint32_t bar_up_done(uint32_t base) { return base + 8 * (2 * NST + 2 * NMS); }
 
+// Message of a tip child for this thread's two sites (+ optionally Q P(t) e_mask for the gradient).
+template <bool CLIP, bool WITH_Q>
+__device__ __forceinline__ void tip_messages(const double* P, const double* QP, const unsigned char* crow, double (&m)[NS][4],
+                                             double (&q)[NS][4]) {
+  const uchar2 rr = *reinterpret_cast<const uchar2*>(crow);
+  tip_columns(P, rr.x, m[0]);
+  tip_columns(P, rr.y, m[1]);
+  if (WITH_Q) {
+    tip_columns(QP, rr.x, q[0]);
+    tip_columns(QP, rr.y, q[1]);
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[s][i] = clipv<CLIP>(m[s][i]);
+}
+
 // One work item for the four consumer warps.
 template <bool WANT_GRAD, bool CLIP>
 __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char* smem, RingState& rs, int u, int tile,
@@ -160,18 +228,19 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
   const uint32_t bars = smem_u32(smem);
   double* stk = reinterpret_cast<double*>(smem + OFF_STK);  // [depth][4][TILE]
   double* gst = stk + (size_t)p.depth * 4 * TILE;           // [GCH][GROW]
-  double* red = gst + GCH * GROW;                           // [TILE]
+  double* red = gst + GCH * GROW;                           // [CT]
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int n = p.n;
   const int nsteps = n - 1;
-  const long long s = (long long)tile * TILE + tid;
-  const double cnt = p.counts[(size_t)t * p.S_pad + s];
+  const long long s0 = (long long)tile * TILE + NS * tid;
+  const double2 cnt2 = *reinterpret_cast<const double2*>(p.counts + (size_t)t * p.S_pad + s0);
+  const double cnt[NS] = {cnt2.x, cnt2.y};
 
   // ------------------------------------------------------------------ up pass (prune.py:15-49)
-  double sc = 1.0;
-  int ex = 0;
-  double ll_site = 0.0;
+  double sc[NS] = {1.0, 1.0};
+  int ex[NS] = {0, 0};
+  double ll_site[NS] = {0.0, 0.0};
   for (int c0 = 0; c0 < nsteps; c0 += CH) {
     const unsigned char* stage = smem + OFF_STAGE + rs.cst * STAGE_BYTES;
     mbar_wait(bar_full_c(bars, rs.cst), rs.cph);
@@ -179,57 +248,61 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
     for (int k = 0; k < cn; ++k) {
       const double* rec = reinterpret_cast<const double*>(stage) + k * UPREC;
       const int4 op = *reinterpret_cast<const int4*>(rec);
-      const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + tid;
-      double ma[4], mb[4];
-      if (op.w & 1) {
-        const int r = crow[0];
-        tip_columns(rec + 2, r, __all_sync(0xffffffffu, r < 4), ma);
+      const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + NS * tid;
+      double ma[NS][4], mb[NS][4], dummy[NS][4];
+      if (op.w & 1)
+        tip_messages<CLIP, false>(rec + UP_A, nullptr, crow, ma, dummy);
+      else
+        load_rows(stk + (op.z & 0xff) * (4 * TILE) + NS * tid, ma);
+      if (op.w & 2)
+        tip_messages<CLIP, false>(rec + UP_B, nullptr, crow + CODE_ROW, mb, dummy);
+      else
+        load_rows(stk + ((op.z >> 8) & 0xff) * (4 * TILE) + NS * tid, mb);
+      double pr[NS][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ma[i] = clipv<CLIP>(ma[i]);
-      } else {
-        const double* src = stk + (op.z & 0xff) * (4 * TILE) + tid;
+      for (int s = 0; s < NS; ++s)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ma[i] = src[i * TILE];
-      }
-      if (op.w & 2) {
-        const int r = crow[CODE_ROW];
-        tip_columns(rec + 18, r, __all_sync(0xffffffffu, r < 4), mb);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mb[i] = clipv<CLIP>(mb[i]);
-      } else {
-        const double* src = stk + ((op.z >> 8) & 0xff) * (4 * TILE) + tid;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mb[i] = src[i * TILE];
-      }
-      double pr[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pr[i] = ma[i] * mb[i];
+        for (int i = 0; i < 4; ++i) pr[s][i] = ma[s][i] * mb[s][i];
       if (op.w & 4) {
         // log(post[root] . pi) + const[root]  (prune.py:131) with post = Pprod / c folded in
-        const double like = (pr[0] * p.pi[0] + pr[1] * p.pi[1]) + (pr[2] * p.pi[2] + pr[3] * p.pi[3]);
-        ll_site = log(like * sc) + (double)ex * 0.6931471805599453094;
-      } else {
-        const double c = (pr[0] + pr[1]) + (pr[2] + pr[3]);
-        const double inv = 1.0 / c;
-        sc *= c;
-        {
-          const int hi = __double2hiint(sc);
-          const int e = (hi >> 20) - 1023;
-          ex += e;
-          sc = __hiloint2double(hi - (e << 20), __double2loint(sc));
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const double like = (pr[s][0] * p.pi[0] + pr[s][1] * p.pi[1]) + (pr[s][2] * p.pi[2] + pr[s][3] * p.pi[3]);
+          ll_site[s] = log(CLIP ? like * sc[s] : like) + (double)ex[s] * 0.6931471805599453094;
         }
-        double post[4];
+      } else {
+        double post[NS][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) post[i] = pr[i] * inv;
+        for (int s = 0; s < NS; ++s) {
+          const double c = (pr[s][0] + pr[s][1]) + (pr[s][2] + pr[s][3]);
+          if (CLIP) {
+            const double inv = 1.0 / c;  // Pprod /= c (prune.py:34)
+            sc[s] *= c;
+            const int e = exponent_of(sc[s]);
+            ex[s] += e;
+            sc[s] = scale_pow2(sc[s], e);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) post[s][i] = pr[s][i] * inv;
+          } else {
+            const int e = exponent_of(c);  // rescale by 2^-e: exact, sum ends up in [1, 2)
+            ex[s] += e;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) post[s][i] = scale_pow2(pr[s][i], e);
+          }
+        }
         double M[16];
-        lds16(rec + 34, M);
-        double* dst = stk + ((op.z >> 16) & 0xff) * (4 * TILE) + tid;
-        double* gdst = myscr + (size_t)(c0 + k) * (4 * TILE);
+        lds16(rec + UP_P, M);
+        double v[NS][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double v = clipv<CLIP>(M[i * 4 + 0] * post[0] + M[i * 4 + 1] * post[1] + M[i * 4 + 2] * post[2] + M[i * 4 + 3] * post[3]);
-          dst[i * TILE] = v;
-          if (WANT_GRAD) __stcg(gdst + i * TILE, v);
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[s][i] = clipv<CLIP>(M[i * 4 + 0] * post[s][0] + M[i * 4 + 1] * post[s][1] + M[i * 4 + 2] * post[s][2] + M[i * 4 + 3] * post[s][3]);
+        store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, v);
+        if (WANT_GRAD) {
+          double* gdst = myscr + (size_t)(c0 + k) * (4 * TILE);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) __stcg(reinterpret_cast<double2*>(gdst + i * TILE), make_double2(v[0][i], v[1][i]));
         }
       }
     }
@@ -243,10 +316,14 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_up_done(bars));
   }
-  if (p.site_ll != nullptr && s < p.S) p.site_ll[(size_t)u * p.S + s] = ll_site;
+  if (p.site_ll != nullptr) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (s0 + s < p.S) p.site_ll[(size_t)u * p.S + s0 + s] = ll_site[s];
+  }
   {
     // sum_s counts[s] * ll_s over the tile (bdsky.py:341)
-    double v = cnt * ll_site;
+    double v = cnt[0] * ll_site[0] + cnt[1] * ll_site[1];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     consumer_bar();
@@ -271,105 +348,122 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
       const int step = c0 + k;
       const double* rec = reinterpret_cast<const double*>(stage) + k * DNREC;
       const int4 op = *reinterpret_cast<const int4*>(rec);
-      const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + tid;
+      const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + NS * tid;
       const int sp = op.z & 0xff;
-      double pre[4];
+      double pre[NS][4];
       if (sp == 0xff) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pre[i] = p.pi[i];  // pre[root] = pi (prune.py:88)
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pre[s][i] = p.pi[i];  // pre[root] = pi (prune.py:88)
       } else {
-        const double* src = stk + sp * (4 * TILE) + tid;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pre[i] = src[i * TILE];
+        load_rows(stk + sp * (4 * TILE) + NS * tid, pre);
       }
-      double ma[4], mb[4], qa[4], qb[4];
+      double ma[NS][4], mb[NS][4], qa[NS][4], qb[NS][4];
       if (op.w & 1) {
-        const int r = crow[0];
-        const bool simple = __all_sync(0xffffffffu, r < 4);
-        tip_columns(rec + 2, r, simple, ma);
-        tip_columns(rec + 34, r, simple, qa);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ma[i] = clipv<CLIP>(ma[i]);
+        tip_messages<CLIP, true>(rec + DN_A, rec + DN_QA, crow, ma, qa);
       } else {
         mbar_wait(bar_full_m(bars, rs.mst), rs.mph);
-        const double* src = reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + tid;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ma[i] = src[i * TILE];
+        load_rows(reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + NS * tid, ma);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty_m(bars, rs.mst));
         rs.adv_m();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) qa[i] = p.Q[i * 4 + 0] * ma[0] + p.Q[i * 4 + 1] * ma[1] + p.Q[i * 4 + 2] * ma[2] + p.Q[i * 4 + 3] * ma[3];
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            qa[s][i] = p.Q[i * 4 + 0] * ma[s][0] + p.Q[i * 4 + 1] * ma[s][1] + p.Q[i * 4 + 2] * ma[s][2] + p.Q[i * 4 + 3] * ma[s][3];
       }
       if (op.w & 2) {
-        const int r = crow[CODE_ROW];
-        const bool simple = __all_sync(0xffffffffu, r < 4);
-        tip_columns(rec + 18, r, simple, mb);
-        tip_columns(rec + 50, r, simple, qb);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mb[i] = clipv<CLIP>(mb[i]);
+        tip_messages<CLIP, true>(rec + DN_B, rec + DN_QB, crow + CODE_ROW, mb, qb);
       } else {
         mbar_wait(bar_full_m(bars, rs.mst), rs.mph);
-        const double* src = reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + tid;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mb[i] = src[i * TILE];
+        load_rows(reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + NS * tid, mb);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty_m(bars, rs.mst));
         rs.adv_m();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) qb[i] = p.Q[i * 4 + 0] * mb[0] + p.Q[i * 4 + 1] * mb[1] + p.Q[i * 4 + 2] * mb[2] + p.Q[i * 4 + 3] * mb[3];
-      }
-      double wa[4], wb[4];
+        for (int s = 0; s < NS; ++s)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) wa[i] = pre[i] * mb[i], wb[i] = pre[i] * ma[i];
-      const double den = (wa[0] * ma[0] + wa[1] * ma[1]) + (wa[2] * ma[2] + wa[3] * ma[3]);
-      const double rden = cnt / den;
-      const double ga = ((wa[0] * qa[0] + wa[1] * qa[1]) + (wa[2] * qa[2] + wa[3] * qa[3])) * rden;
-      const double gb = ((wb[0] * qb[0] + wb[1] * qb[1]) + (wb[2] * qb[2] + wb[3] * qb[3])) * rden;
+          for (int i = 0; i < 4; ++i)
+            qb[s][i] = p.Q[i * 4 + 0] * mb[s][0] + p.Q[i * 4 + 1] * mb[s][1] + p.Q[i * 4 + 2] * mb[s][2] + p.Q[i * 4 + 3] * mb[s][3];
+      }
+      double wa[NS][4], wb[NS][4];
+      int ed[NS];
       const int gslot = (2 * step) & (GCH - 1);
-      gst[gslot * GROW + tid] = ga;
-      gst[(gslot + 1) * GROW + tid] = gb;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wa[s][i] = pre[s][i] * mb[s][i], wb[s][i] = pre[s][i] * ma[s][i];
+        const double den = (wa[s][0] * ma[s][0] + wa[s][1] * ma[s][1]) + (wa[s][2] * ma[s][2] + wa[s][3] * ma[s][3]);
+        ed[s] = exponent_of(den);
+        const double rden = cnt[s] * rcp_pos(den);
+        const double ga = ((wa[s][0] * qa[s][0] + wa[s][1] * qa[s][1]) + (wa[s][2] * qa[s][2] + wa[s][3] * qa[s][3])) * rden;
+        const double gb = ((wb[s][0] * qb[s][0] + wb[s][1] * qb[s][1]) + (wb[s][2] * qb[s][2] + wb[s][3] * qb[s][3])) * rden;
+        gst[gslot * GROW + NS * tid + s] = ga;
+        gst[(gslot + 1) * GROW + NS * tid + s] = gb;
+      }
 
       if (!(op.w & 1)) {
         double M[16];
-        lds16(rec + 2, M);
-        double B[4];
+        lds16(rec + DN_A, M);
+        double B[NS][4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) B[v] = clipv<CLIP>(wa[0] * M[0 * 4 + v] + wa[1] * M[1 * 4 + v] + wa[2] * M[2 * 4 + v] + wa[3] * M[3 * 4 + v]);
-        const double inv = 1.0 / ((B[0] + B[1]) + (B[2] + B[3]));
-        double* dst = stk + ((op.z >> 8) & 0xff) * (4 * TILE) + tid;
+        for (int s = 0; s < NS; ++s) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) dst[v * TILE] = B[v] * inv;
+          for (int v = 0; v < 4; ++v)
+            B[s][v] = clipv<CLIP>(wa[s][0] * M[0 * 4 + v] + wa[s][1] * M[1 * 4 + v] + wa[s][2] * M[2 * 4 + v] + wa[s][3] * M[3 * 4 + v]);
+          if (CLIP) {
+            const double inv = 1.0 / ((B[s][0] + B[s][1]) + (B[s][2] + B[s][3]));  // B /= c (prune.py:74)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) B[s][v] *= inv;
+          } else {
+            // any positive rescaling cancels in g = num/den; 2^-exponent(den) keeps pre within ~[1, 1e20]
+#pragma unroll
+            for (int v = 0; v < 4; ++v) B[s][v] = scale_pow2(B[s][v], ed[s]);
+          }
+        }
+        store_rows(stk + ((op.z >> 8) & 0xff) * (4 * TILE) + NS * tid, B);
       }
       if (!(op.w & 2)) {
         double M[16];
-        lds16(rec + 18, M);
-        double B[4];
+        lds16(rec + DN_B, M);
+        double B[NS][4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) B[v] = clipv<CLIP>(wb[0] * M[0 * 4 + v] + wb[1] * M[1 * 4 + v] + wb[2] * M[2 * 4 + v] + wb[3] * M[3 * 4 + v]);
-        const double inv = 1.0 / ((B[0] + B[1]) + (B[2] + B[3]));
-        double* dst = stk + ((op.z >> 16) & 0xff) * (4 * TILE) + tid;
+        for (int s = 0; s < NS; ++s) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) dst[v * TILE] = B[v] * inv;
+          for (int v = 0; v < 4; ++v)
+            B[s][v] = clipv<CLIP>(wb[s][0] * M[0 * 4 + v] + wb[s][1] * M[1 * 4 + v] + wb[s][2] * M[2 * 4 + v] + wb[s][3] * M[3 * 4 + v]);
+          if (CLIP) {
+            const double inv = 1.0 / ((B[s][0] + B[s][1]) + (B[s][2] + B[s][3]));
+#pragma unroll
+            for (int v = 0; v < 4; ++v) B[s][v] *= inv;
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) B[s][v] = scale_pow2(B[s][v], ed[s]);
+          }
+        }
+        store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, B);
       }
 
       if (gslot + 2 == GCH || step == nsteps - 1) {
-        // transposed reduction of the staged chunk over the tile's sites
+        // transposed reduction of the staged round over the tile's sites
         const int nval = gslot + 2;
         consumer_bar();
-        const int r = tid & (GCH - 1), q = tid / GCH;
+        const int r = tid & (GCH - 1), q = tid / GCH;  // CT/GCH column groups of TILE/(CT/GCH) sites
+        constexpr int COLS = TILE / (CT / GCH);
         double acc = 0.0;
         if (r < nval) {
-          const double* row = gst + r * GROW + q * GCH;
+          const double* row = gst + r * GROW + q * COLS;
 #pragma unroll
-          for (int kk = 0; kk < GCH; ++kk) acc += row[kk];
+          for (int kk = 0; kk < COLS; ++kk) acc += row[kk];
         }
         red[q * GCH + r] = acc;
         consumer_bar();
         if (tid < nval) {
           double tot = 0.0;
 #pragma unroll
-          for (int kk = 0; kk < TILE / GCH; ++kk) tot += red[kk * GCH + tid];
+          for (int kk = 0; kk < CT / GCH; ++kk) tot += red[kk * GCH + tid];
           gout[2 * step + 2 - nval + tid] = tot;
         }
       }
@@ -382,7 +476,7 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
 }
 
 template <bool WANT_GRAD>
-__global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) {
+__global__ void __launch_bounds__(THREADS, 2) prune_kernel(const PruneParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t bars = smem_u32(smem);
   const int tid = threadIdx.x;
@@ -399,9 +493,9 @@ __global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) 
   RingState rs;
   const unsigned char* scr_base = reinterpret_cast<const unsigned char*>(p.scratch) + (size_t)blockIdx.x * nsteps * MSG_BYTES;
 
-  if (tid >= TILE) {
+  if (tid >= CT) {
     // =============================================================== producer warp (one lane)
-    if (tid != TILE) return;
+    if (tid != CT) return;
     uint32_t up_phase = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       const int u = (int)(item / p.tiles);
@@ -411,7 +505,7 @@ __global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) 
       const unsigned char* cup = p.codes_up + ((size_t)t * p.tiles + tile) * (size_t)(2 * nsteps) * CODE_ROW;
       for (int c0 = 0; c0 < nsteps; c0 += CH) {
         const int cn = min(CH, nsteps - c0);
-        mbar_wait(bar_empty_c(bars, rs.cst), rs.cph ^ 1);
+        mbar_wait_sleep(bar_empty_c(bars, rs.cst), rs.cph ^ 1);
         const uint32_t dst = smem_u32(smem + OFF_STAGE + rs.cst * STAGE_BYTES);
         const uint32_t full = bar_full_c(bars, rs.cst);
         mbar_expect_tx(full, cn * (UPREC * 8 + 2 * CODE_ROW));
@@ -425,12 +519,12 @@ __global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) 
       const int nchunks = (nsteps + CH - 1) / CH;
       const int32_t* mrows = p.msg_rows + (size_t)t * max(n - 2, 1);
       const int32_t* mstart = p.msg_start + (size_t)t * (nchunks + 1);
-      mbar_wait(bar_up_done(bars), up_phase);  // every consumer warp has finished (and fenced) its scratch stores
+      mbar_wait_sleep(bar_up_done(bars), up_phase);  // every consumer warp has finished (and fenced) its scratch stores
       up_phase ^= 1;
       int mi = 0;
       for (int c0 = 0, c = 0; c0 < nsteps; c0 += CH, ++c) {
         const int cn = min(CH, nsteps - c0);
-        mbar_wait(bar_empty_c(bars, rs.cst), rs.cph ^ 1);
+        mbar_wait_sleep(bar_empty_c(bars, rs.cst), rs.cph ^ 1);
         const uint32_t dst = smem_u32(smem + OFF_STAGE + rs.cst * STAGE_BYTES);
         const uint32_t full = bar_full_c(bars, rs.cst);
         mbar_expect_tx(full, cn * (DNREC * 8 + 2 * CODE_ROW));
@@ -440,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) 
         const int mend = mstart[c + 1];
         for (; mi < mend; ++mi) {
           const int row = mrows[mi];
-          mbar_wait(bar_empty_m(bars, rs.mst), rs.mph ^ 1);
+          mbar_wait_sleep(bar_empty_m(bars, rs.mst), rs.mph ^ 1);
           const uint32_t mfull = bar_full_m(bars, rs.mst);
           mbar_expect_tx(mfull, MSG_BYTES);
           bulk_g2s(smem_u32(smem + OFF_MSG + rs.mst * MSG_BYTES), scr_base + (size_t)row * MSG_BYTES, MSG_BYTES, mfull);
@@ -452,7 +546,7 @@ __global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) 
   }
 
   // ================================================================= consumer warps
-  double* myscr = p.scratch + (size_t)blockIdx.x * nsteps * (4 * TILE) + tid;
+  double* myscr = p.scratch + (size_t)blockIdx.x * nsteps * (4 * TILE) + NS * tid;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     const int u = (int)(item / p.tiles);
     const int tile = (int)(item - (long long)u * p.tiles);
@@ -478,7 +572,7 @@ struct TablesParams {
 };
 
 // P(t) = U diag(exp(d t)) Uinv (substitution.py:61-62); optionally Q P(t) = U diag(d exp(d t)) Uinv.
-__device__ __forceinline__ bool expm16(const vbsky_subst_model& m, double t, double* P, double* QP) {
+__device__ __forceinline__ bool expm16(const vbsky_subst_model& m, double t, bool tip, double* P, double* QP) {
   // Entries are accumulated as delta_ij + sum_k U_ik expm1(d_k t) Uinv_kj: for the short branches of
   // real data (t ~ 1e-6..1e-3) the off-diagonals of sum_k U_ik exp(d_k t) Uinv_kj are the remainder of
   // O(1) terms cancelling, i.e. carry ~1e-16/t relative rounding noise (as the reference's own
@@ -498,10 +592,22 @@ __device__ __forceinline__ bool expm16(const vbsky_subst_model& m, double t, dou
         s += uu * e1[k];
         q += (m.d[k] * uu) * (e1[k] + 1.0);
       }
-      P[i * 4 + j] = s;
-      if (QP) QP[i * 4 + j] = q;
+      if (tip) {
+        P[j * 4 + i] = s;  // column-major
+        if (QP) QP[j * 4 + i] = q;
+      } else {
+        P[i * 4 + j] = s;
+      }
       small |= !(s >= 1e-20) || !(s <= 2.0);  // also catches NaN / inf
     }
+  if (tip) {
+    // fifth column: the fully ambiguous state set (sum of the four columns, in the reference's order of addition)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      P[16 + i] = ((P[i] + P[4 + i]) + P[8 + i]) + P[12 + i];
+      if (QP) QP[16 + i] = ((QP[i] + QP[4 + i]) + QP[8 + i]) + QP[12 + i];
+    }
+  }
   return small;
 }
 
@@ -518,17 +624,17 @@ __global__ void tables_kernel(const TablesParams p) {
     double* rec = p.uptab + idx * UPREC;
     *reinterpret_cast<int4*>(rec) = make_int4(op.x, op.y, op.z, op.w);
     const int a = op.x & 0xffff, b = (op.x >> 16) & 0xffff;
-    if (op.w & 1) small |= expm16(p.mdl, bl[a], rec + 2, nullptr);
-    if (op.w & 2) small |= expm16(p.mdl, bl[b], rec + 18, nullptr);
-    if (!(op.w & 4)) small |= expm16(p.mdl, bl[op.y], rec + 34, nullptr);
+    if (op.w & 1) small |= expm16(p.mdl, bl[a], true, rec + UP_A, nullptr);
+    if (op.w & 2) small |= expm16(p.mdl, bl[b], true, rec + UP_B, nullptr);
+    if (!(op.w & 4)) small |= expm16(p.mdl, bl[op.y], false, rec + UP_P, nullptr);
   }
   if (p.want_grad) {
     const Op op = p.down[(size_t)t * nsteps + step];
     double* rec = p.dntab + idx * DNREC;
     *reinterpret_cast<int4*>(rec) = make_int4(op.x, op.y, op.z, op.w);
     const int a = op.x & 0xffff, b = (op.x >> 16) & 0xffff;
-    small |= expm16(p.mdl, bl[a], rec + 2, (op.w & 1) ? rec + 34 : nullptr);
-    small |= expm16(p.mdl, bl[b], rec + 18, (op.w & 2) ? rec + 50 : nullptr);
+    small |= expm16(p.mdl, bl[a], (op.w & 1) != 0, rec + DN_A, (op.w & 1) ? rec + DN_QA : nullptr);
+    small |= expm16(p.mdl, bl[b], (op.w & 2) != 0, rec + DN_B, (op.w & 2) ? rec + DN_QB : nullptr);
   }
   if (small) atomicOr(p.flags + u, 1u);
 }
