@@ -99,3 +99,38 @@ def test_prune_caterpillar_and_ambiguity(cuda):
         np.testing.assert_allclose(ll[u].item(), tot, rtol=LL_RTOL)
         np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
     ens.close()
+
+
+def test_prune_zero_length_branches_use_literal_clips(cuda):
+    """Branch lengths of exactly 0 (and 1e-30) make P(t) entries vanish, so the 1e-40 clips of
+    substitution.py:70 become active; those units take the kernel's literal-clip variant."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, codes_to_partials
+    from vbsky_b200.synth import evolve_codes, random_tree, sample_heights
+    from vbsky_b200.tips import PackedTips
+
+    rng = np.random.default_rng(9)
+    n, S = 14, 300
+    td = random_tree(n, rng)
+    Q, oQ = HKY(2.7), osub.HKY(2.7)
+    sh = sample_heights(td, 3, rng, origin=1.0)
+    bl = sh.branch_lengths * 0.1
+    codes = evolve_codes(td, bl[0], oQ, S, rng, missing=0.02)
+    bl[0, [0, 3, n + 1]] = 0.0        # tip and internal branches of zero length
+    bl[1, [1, 2]] = 1e-30             # far below the 1e-20 threshold
+    # unit 2 stays regular (clip-free variant) in the same launch
+    tips = PackedTips(codes, np.ones(S))
+    ens = Ensemble([td], [tips], Q, device=cuda)
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), torch.zeros(3, dtype=torch.int32, device=cuda),
+                              want_grad=True, want_site_ll=True)
+    for u in range(3):
+        tot, g, sll = oprune.data_loglik_and_grad(bl[u], oQ, codes_to_partials(codes), tips.counts, _oracle_td(td))
+        assert np.isfinite(sll).all()
+        np.testing.assert_allclose(site[u].cpu().numpy(), sll, rtol=LL_RTOL, atol=LL_ATOL)
+        np.testing.assert_allclose(ll[u].item(), tot, rtol=LL_RTOL)
+        # eq. (9) and its scale-free form agree wherever no clip binds; sites that hit a clip have
+        # likelihood ~1e-40 and meaningless derivatives in both, so compare on the clip-free sites
+        ok = sll > -80.0
+        if ok.all():
+            np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    ens.close()

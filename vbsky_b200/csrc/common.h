@@ -40,7 +40,7 @@ struct Op {
 
 // Geometry shared by the host-side layout builder and the pruning kernel.
 constexpr int kTile = 256;        // site patterns per CTA tile (two per consumer thread)
-constexpr int kChunkSteps = 4;    // schedule steps delivered per ring stage
+constexpr int kChunkSteps = 3;    // schedule steps delivered per ring stage
 
 }  // namespace vbsky
 

@@ -44,8 +44,8 @@ constexpr int CT = TILE / NS;         // consumer threads
 constexpr int NCW = CT / 32;          // consumer warps
 constexpr int THREADS = CT + 32;      // + producer warp
 constexpr int CH = kChunkSteps;       // steps per ring stage
-constexpr int NST = 3;                // step-chunk ring stages
-constexpr int NMS = 3;                // message ring slots
+constexpr int NST = 2;                // step-chunk ring stages
+constexpr int NMS = 2;                // message ring slots
 constexpr int TIPM = 20;              // doubles of a tip-branch table: columns of P(t) for A,C,G,T and their sum (N)
 constexpr int UPREC = 2 + 2 * TIPM + 16;  // up-step record:   op(2) Ta(20) Tb(20) Pp(16)
 constexpr int DNREC = 2 + 4 * TIPM;       // down-step record: op(2) Ta|Pa(20) Tb|Pb(20) QTa(20) QTb(20)
@@ -56,7 +56,7 @@ constexpr int STAGE_BYTES = CH * DNREC * 8 + 2 * CH * CODE_ROW;
 constexpr int STAGE_CODES = CH * DNREC * 8;  // byte offset of the code rows inside a stage
 constexpr int MSG_BYTES = 4 * TILE * 8;
 constexpr int GCH = 8;                // branch gradients staged per reduction round
-constexpr int GROW = TILE + 1;
+constexpr int GROW = CT + 1;          // one staged value per consumer thread (its two sites pre-added)
 constexpr int OFF_STAGE = 128;
 constexpr int OFF_MSG = OFF_STAGE + ((NST * STAGE_BYTES + 127) / 128) * 128;
 constexpr int OFF_STK = OFF_MSG + NMS * MSG_BYTES;
@@ -390,6 +390,7 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
       }
       double wa[NS][4], wb[NS][4];
       int ed[NS];
+      double gsum_a = 0.0, gsum_b = 0.0;
       const int gslot = (2 * step) & (GCH - 1);
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
@@ -400,9 +401,10 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
         const double rden = cnt[s] * rcp_pos(den);
         const double ga = ((wa[s][0] * qa[s][0] + wa[s][1] * qa[s][1]) + (wa[s][2] * qa[s][2] + wa[s][3] * qa[s][3])) * rden;
         const double gb = ((wb[s][0] * qb[s][0] + wb[s][1] * qb[s][1]) + (wb[s][2] * qb[s][2] + wb[s][3] * qb[s][3])) * rden;
-        gst[gslot * GROW + NS * tid + s] = ga;
-        gst[(gslot + 1) * GROW + NS * tid + s] = gb;
+        gsum_a += ga, gsum_b += gb;
       }
+      gst[gslot * GROW + tid] = gsum_a;
+      gst[(gslot + 1) * GROW + tid] = gsum_b;
 
       if (!(op.w & 1)) {
         double M[16];
@@ -450,8 +452,8 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
         // transposed reduction of the staged round over the tile's sites
         const int nval = gslot + 2;
         consumer_bar();
-        const int r = tid & (GCH - 1), q = tid / GCH;  // CT/GCH column groups of TILE/(CT/GCH) sites
-        constexpr int COLS = TILE / (CT / GCH);
+        const int r = tid & (GCH - 1), q = tid / GCH;  // CT/GCH column groups of GCH threads' values
+        constexpr int COLS = GCH;
         double acc = 0.0;
         if (r < nval) {
           const double* row = gst + r * GROW + q * COLS;
@@ -475,8 +477,11 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
   consumer_bar();  // red / gst are reused by the next item
 }
 
-template <bool WANT_GRAD>
-__global__ void __launch_bounds__(THREADS, 2) prune_kernel(const PruneParams p) {
+// Each launch handles the units whose clip flag equals CLIP and skips the others (two launches per
+// evaluation; the literal-clip one normally finds nothing to do).  Keeping one arithmetic variant per
+// kernel halves the code the instruction cache has to hold.
+template <bool WANT_GRAD, bool CLIP>
+__global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t bars = smem_u32(smem);
   const int tid = threadIdx.x;
@@ -499,6 +504,7 @@ __global__ void __launch_bounds__(THREADS, 2) prune_kernel(const PruneParams p) 
     uint32_t up_phase = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       const int u = (int)(item / p.tiles);
+      if (((p.flags[u] & 1u) != 0) != CLIP) continue;
       const int tile = (int)(item - (long long)u * p.tiles);
       const int t = p.unit_tree[u];
       const unsigned char* utab = reinterpret_cast<const unsigned char*>(p.uptab) + (size_t)u * nsteps * (UPREC * 8);
@@ -551,10 +557,8 @@ __global__ void __launch_bounds__(THREADS, 2) prune_kernel(const PruneParams p) 
     const int u = (int)(item / p.tiles);
     const int tile = (int)(item - (long long)u * p.tiles);
     const int t = p.unit_tree[u];
-    if (p.flags[u] & 1u)
-      consume_item<WANT_GRAD, true>(p, smem, rs, u, tile, t, myscr);
-    else
-      consume_item<WANT_GRAD, false>(p, smem, rs, u, tile, t, myscr);
+    if (((p.flags[u] & 1u) != 0) != CLIP) continue;
+    consume_item<WANT_GRAD, CLIP>(p, smem, rs, u, tile, t, myscr);
   }
 }
 
@@ -687,13 +691,19 @@ static int prune_config(const vbsky_layout* lay, const vbsky_tips* tips, int U, 
   VB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if (cfg->smem > (size_t)max_smem)
     return set_error(VBSKY_EINVAL, "tree needs %d live vectors (%zu B shared memory) but the device offers %d B", cfg->depth, cfg->smem, max_smem);
+  int per_sm2 = 0;
   if (want_grad) {
-    VB_CUDA(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<true>, THREADS, cfg->smem));
+    VB_CUDA(cudaFuncSetAttribute(prune_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
+    VB_CUDA(cudaFuncSetAttribute(prune_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<true, false>, THREADS, cfg->smem));
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, prune_kernel<true, true>, THREADS, cfg->smem));
   } else {
-    VB_CUDA(cudaFuncSetAttribute(prune_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<false>, THREADS, cfg->smem));
+    VB_CUDA(cudaFuncSetAttribute(prune_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
+    VB_CUDA(cudaFuncSetAttribute(prune_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<false, false>, THREADS, cfg->smem));
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, prune_kernel<false, true>, THREADS, cfg->smem));
   }
+  per_sm = std::min(per_sm, per_sm2);
   if (per_sm < 1) return set_error(VBSKY_ECUDA, "pruning kernel cannot be resident (smem %zu B)", cfg->smem);
   const long long items = (long long)U * cfg->tiles;
   const long long slots = (long long)sms * per_sm;
@@ -774,20 +784,26 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
     VB_CUDA(cudaEventRecord(ev0, stream));
   }
   if (want_grad)
-    prune_kernel<true><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
+    prune_kernel<true, false><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
   else
-    prune_kernel<false><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
+    prune_kernel<false, false><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
   VB_CUDA(cudaGetLastError());
   if (g_timing.enabled) {
     VB_CUDA(cudaEventRecord(ev1, stream));
     g_timing.pending.push_back({ev0, ev1});
   }
+  // units with a (near-)zero branch length: literal clip arithmetic
+  if (want_grad)
+    prune_kernel<true, true><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
+  else
+    prune_kernel<false, true><<<cfg.grid, THREADS, cfg.smem, stream>>>(p);
+  VB_CUDA(cudaGetLastError());
   {
     dim3 grid((unsigned)U, (unsigned)((2 * n - 2 + 127) / 128));
     finalize_kernel<<<grid, 128, 0, stream>>>(p.ll_part, p.g_part, unit_tree, lay->d_down_nodes, U, n, cfg.tiles, ll, dll_dbl);
     VB_CUDA(cudaGetLastError());
   }
-  g_stats[0] = 3, g_stats[1] = cfg.grid, g_stats[2] = TILE, g_stats[3] = (int64_t)cfg.smem;
+  g_stats[0] = 4, g_stats[1] = cfg.grid, g_stats[2] = TILE, g_stats[3] = (int64_t)cfg.smem;
   {
     // Algorithmic HBM bytes of prune_kernel: every non-root internal message written once and read
     // once (32 B per site), tip codes 1 B per tip-site and pass, counts, per-site ll out, per-tile gradient
