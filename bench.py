@@ -165,6 +165,7 @@ def main():
     import torch.distributed as dist
 
     from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.parallel import allreduce_elbo, pack_global, shard_units
     from vbsky_b200.substitution import HKY
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,7 +185,7 @@ def main():
     ens = Ensemble(data.tds, data.tips, Q, device=dev)
     # (tree, sample) units, round-robin over ranks
     units = [(t, k) for t in range(T) for k in range(K)]
-    mine = units[rank::world]
+    mine = shard_units(T, K, rank, world)
     U = len(mine)
     m = M_INTERVALS
     rng = np.random.default_rng(12345)
@@ -204,19 +205,13 @@ def main():
     ut = torch.as_tensor(ut_host, device=dev)
     grads = {k: torch.empty_like(params[k]) for k in Ensemble.GRAD_KEYS}
     out = {k: torch.empty(U, dtype=torch.float64, device=dev) for k in ("ll", "tree", "data")}
-    GLOBAL = ("origin", "clock_rate", "R", "delta", "s", "rho")
     red = torch.zeros(1 + 2 + 4 * m, dtype=torch.float64, device=dev)
 
     def step():
         # ELBO likelihood part: mean over the K samples of loglik, summed over trees (optim.py:72-75, fasta.py:456-487
         # batched over the ensemble), and its gradient; gradients of the per-tree (local) parameters stay on their owner.
         ens.loglik_device(params, ut, m, flags=7, grads=grads, out=out)
-        red[0] = out["ll"].sum() / K
-        red[1] = grads["origin"].sum() / K
-        red[2] = grads["clock_rate"].sum() / K
-        torch.sum(torch.stack([grads["R"], grads["delta"], grads["s"], grads["rho"]], 0), dim=1, out=red[3:].view(4, m))
-        if world > 1:
-            dist.all_reduce(red)
+        allreduce_elbo(pack_global(out["ll"], grads, K, out=red))
 
     for _ in range(max(args.warmup, 3)):
         step()
