@@ -224,11 +224,13 @@ def main():
     ens.kernel_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    torch.cuda.profiler.start()  # lets `ncu --profile-from-start off` capture exactly the timed steps
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)

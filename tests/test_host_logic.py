@@ -149,11 +149,12 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
     scratch = np.full((n - 1, S, 4), np.nan)
     logscale = np.zeros(S)
     ll = None
+    carry = np.full((S, 4), np.nan)
     for step, (x, par, z, w) in enumerate(up):
         a, b = x & 0xFFFF, (x >> 16) & 0xFFFF
         assert bool(w & 1) == (a < n) and bool(w & 2) == (b < n) and bool(w & 4) == (par == root)
-        ma = Q.expm_action(bl[a], partials[:, a]) if w & 1 else stack[z & 0xFF].copy()
-        mb = Q.expm_action(bl[b], partials[:, b]) if w & 2 else stack[(z >> 8) & 0xFF].copy()
+        ma = Q.expm_action(bl[a], partials[:, a]) if w & 1 else (carry.copy() if w & 8 else stack[z & 0xFF].copy())
+        mb = Q.expm_action(bl[b], partials[:, b]) if w & 2 else (carry.copy() if w & 16 else stack[(z >> 8) & 0xFF].copy())
         assert not np.isnan(ma).any() and not np.isnan(mb).any()
         pr = ma * mb
         if w & 4:
@@ -162,7 +163,9 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
             c = pr.sum(1)
             logscale += np.log(c)
             m = Q.expm_action(bl[par], pr / c[:, None])
-            stack[(z >> 16) & 0xFF] = m
+            carry = m
+            if w & 32:
+                stack[(z >> 16) & 0xFF] = m
             scratch[step] = m
     up_row = {int(par): i for i, (_, par, _, _) in enumerate(up)}
     g = np.zeros((S, 2 * n - 2))
@@ -171,8 +174,9 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
         a, b = x & 0xFFFF, (x >> 16) & 0xFFFF
         assert dn[2 * step] == a and dn[2 * step + 1] == b
         sp = z & 0xFF
-        pre = np.tile(Q.pi, (S, 1)) if sp == 0xFF else stack[sp].copy()
-        assert (sp == 0xFF) == (par == root)
+        pre = carry.copy() if w & 8 else (np.tile(Q.pi, (S, 1)) if sp == 0xFF else stack[sp].copy())
+        assert not np.isnan(pre).any()
+        carry = np.full((S, 4), np.nan)
         ma = Q.expm_action(bl[a], partials[:, a]) if w & 1 else scratch[up_row[a]]
         mb = Q.expm_action(bl[b], partials[:, b]) if w & 2 else scratch[up_row[b]]
         # Q m_c: for tips the kernel uses (Q P(t)) e_mask with the unclipped message
@@ -184,10 +188,19 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
         g[:, b] = (wb * qb).sum(1) / den
         if not (w & 1):
             B = Q.expm_action(bl[a], wa, right=False)
-            stack[(z >> 8) & 0xFF] = B / B.sum(1, keepdims=True)
+            B = B / B.sum(1, keepdims=True)
+            if w & 32:
+                stack[(z >> 8) & 0xFF] = B
+            else:
+                carry = B
         if not (w & 2):
             B = Q.expm_action(bl[b], wb, right=False)
-            stack[(z >> 16) & 0xFF] = B / B.sum(1, keepdims=True)
+            B = B / B.sum(1, keepdims=True)
+            if w & 64:
+                stack[(z >> 16) & 0xFF] = B
+            else:
+                assert w & 32 or (w & 1), "only one child's pre vector can be carried"
+                carry = B
     return ll, g
 
 

@@ -50,33 +50,34 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
   const int N = 2 * n - 1, root = N - 1;
   auto internal = [n](int v) { return v >= n; };
 
-  // ---- up pass: need[v] = peak number of live message slots while evaluating subtree v.
+  // ------------------------------------------------------------------------------------ up pass
+  // need[v] = peak number of messages parked in shared memory while evaluating subtree v.  The message
+  // produced by a step is carried in registers into the next step, so only a first-evaluated internal
+  // child waits in a slot while its sibling's subtree is evaluated.
   std::vector<int> need(N, 0), first(N, 0);  // first[v]: which child (0/1) is evaluated first
   for (int v = n; v < N; ++v) {
     const int c[2] = {pc[2 * v], pc[2 * v + 1]};
     int best = 1 << 30, bestf = 0;
     for (int f = 0; f < 2; ++f) {
       const int a = c[f], b = c[1 - f];
-      const int ha = internal(a), hb = internal(b);
-      const int peak = std::max({need[a], ha + need[b], std::max(ha + hb, 1)});
+      // a's result must be parked only if something is evaluated between a and v, i.e. b is internal
+      const int park = (internal(a) && internal(b)) ? 1 : 0;
+      const int peak = std::max(need[a], park + need[b]);
       if (peak < best) best = peak, bestf = f;
     }
     need[v] = best;
     first[v] = bestf;
   }
-  // emit in DFS order (explicit stack: (node, state))
-  std::vector<int> up_row(N, -1), slot_of(N, -1);
+  std::vector<int> order;  // nodes in evaluation order
+  order.reserve(n - 1);
   {
     std::vector<std::pair<int, int>> st;
     st.push_back({root, 0});
-    SlotPool pool;
-    int step = 0;
     while (!st.empty()) {
-      auto& top = st.back();
-      const int v = top.first;
+      const int v = st.back().first;
       const int a = pc[2 * v + first[v]], b = pc[2 * v + 1 - first[v]];
-      if (top.second == 0) {
-        top.second = 1;
+      if (st.back().second == 0) {
+        st.back().second = 1;
         if (internal(a)) {
           st.push_back({a, 0});
           continue;
@@ -89,69 +90,121 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
           continue;
         }
       }
-      // both children done: emit v
-      int sa = 0xff, sb = 0xff, so = 0xff;
-      if (internal(a)) sa = slot_of[a], pool.release(sa);
-      if (internal(b)) sb = slot_of[b], pool.release(sb);
-      if (v != root) so = pool.alloc(), slot_of[v] = so;
-      if (so != 0xff && so >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
-      up[step] = Op{a | (b << 16), v, sa | (sb << 8) | (so << 16),
-                    (internal(a) ? 0 : 1) | (internal(b) ? 0 : 2) | (v == root ? 4 : 0)};
-      up_row[v] = step;
-      ++step;
+      order.push_back(v);
       st.pop_back();
     }
-    if (step != n - 1) return set_error(VBSKY_EINVAL, "internal error: up schedule has %d steps, expected %d", step, n - 1);
+  }
+  if ((int)order.size() != n - 1) return set_error(VBSKY_EINVAL, "internal error: up schedule has %zu steps, expected %d", order.size(), n - 1);
+  std::vector<int> up_row(N, -1), slot_of(N, -1);
+  for (int s = 0; s < n - 1; ++s) up_row[order[s]] = s;
+  std::vector<int> parent(N, -1);
+  for (int v = n; v < N; ++v) parent[pc[2 * v]] = v, parent[pc[2 * v + 1]] = v;
+  {
+    SlotPool pool;
+    for (int s = 0; s < n - 1; ++s) {
+      const int v = order[s];
+      const int a = pc[2 * v + first[v]], b = pc[2 * v + 1 - first[v]];
+      int sa = 0xff, sb = 0xff, so = 0xff, flags = 0;
+      const int ch[2] = {a, b};
+      int* sl[2] = {&sa, &sb};
+      for (int k = 0; k < 2; ++k) {
+        const int c = ch[k];
+        if (!internal(c)) {
+          flags |= 1 << k;  // tip
+        } else if (up_row[c] == s - 1) {
+          flags |= 8 << k;  // result of the previous step, still in registers
+        } else {
+          *sl[k] = slot_of[c];
+          pool.release(slot_of[c]);
+        }
+      }
+      if (v == root) {
+        flags |= 4;
+      } else if (up_row[parent[v]] != s + 1) {
+        so = pool.alloc();  // parked until the sibling's subtree is done
+        slot_of[v] = so;
+        flags |= 0x20;
+        if (so >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
+      }
+      up[s] = Op{a | (b << 16), v, sa | (sb << 8) | (so << 16), flags};
+    }
     *depth_up = std::max(pool.high, 1);
   }
 
-  // ---- down pass: needd[v] = peak live pre-vectors while expanding subtree v (pre_v held on entry).
+  // ---------------------------------------------------------------------------------- down pass
+  // needd[v] = peak number of pre vectors parked while expanding subtree v.  The pre vector of the child
+  // that is expanded next is carried in registers; the other internal child's waits in a slot.
   std::vector<int> needd(N, 0), firstd(N, 0);
   for (int v = n; v < N; ++v) {
     const int a = pc[2 * v], b = pc[2 * v + 1];
     const int ia = internal(a), ib = internal(b);
     if (!ia && !ib)
-      needd[v] = 1;
+      needd[v] = 0;
     else if (ia && !ib)
-      needd[v] = std::max(1, needd[a]), firstd[v] = 0;
+      needd[v] = needd[a], firstd[v] = 0;
     else if (!ia && ib)
-      needd[v] = std::max(1, needd[b]), firstd[v] = 1;
+      needd[v] = needd[b], firstd[v] = 1;
     else {
       // descend first into the child with the smaller need while the other's pre vector waits
       const int f = needd[a] <= needd[b] ? 0 : 1;
       const int cf = pc[2 * v + f], cs = pc[2 * v + 1 - f];
-      needd[v] = std::max({2, needd[cf] + 1, needd[cs]});
+      needd[v] = std::max(needd[cf] + 1, needd[cs]);
       firstd[v] = f;
     }
   }
+  std::vector<int> dorder;
+  dorder.reserve(n - 1);
   {
     std::vector<int> st;
     st.push_back(root);
-    SlotPool pool;
-    std::fill(slot_of.begin(), slot_of.end(), -1);
-    int step = 0, nmsg = 0;
     while (!st.empty()) {
       const int v = st.back();
       st.pop_back();
-      if (step % kChunkSteps == 0) msg_start[step / kChunkSteps] = nmsg;
+      dorder.push_back(v);
       const int a = pc[2 * v + firstd[v]], b = pc[2 * v + 1 - firstd[v]];
-      int sp = 0xff, sa = 0xff, sb = 0xff;
-      if (v != root) sp = slot_of[v], pool.release(sp);
-      if (internal(a)) sa = pool.alloc(), slot_of[a] = sa;
-      if (internal(b)) sb = pool.alloc(), slot_of[b] = sb;
-      if ((sa != 0xff && sa >= 0xff) || (sb != 0xff && sb >= 0xff))
-        return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
-      const int ra = internal(a) ? up_row[a] : 0xffff, rb = internal(b) ? up_row[b] : 0xffff;
-      down[step] = Op{a | (b << 16), v, sp | (sa << 8) | (sb << 16), (internal(a) ? 0 : 1) | (internal(b) ? 0 : 2)};
-      if (internal(a)) msg_rows[nmsg++] = ra;
-      if (internal(b)) msg_rows[nmsg++] = rb;
-      down_nodes[2 * step] = a;
-      down_nodes[2 * step + 1] = b;
-      ++step;
       if (internal(b)) st.push_back(b);
       if (internal(a)) st.push_back(a);  // a is expanded next
     }
-    if (step != n - 1) return set_error(VBSKY_EINVAL, "internal error: down schedule has %d steps", step);
+  }
+  if ((int)dorder.size() != n - 1) return set_error(VBSKY_EINVAL, "internal error: down schedule has %zu steps", dorder.size());
+  {
+    SlotPool pool;
+    std::fill(slot_of.begin(), slot_of.end(), -1);
+    int nmsg = 0;
+    for (int s = 0; s < n - 1; ++s) {
+      const int v = dorder[s];
+      if (s % kChunkSteps == 0) msg_start[s / kChunkSteps] = nmsg;
+      const int a = pc[2 * v + firstd[v]], b = pc[2 * v + 1 - firstd[v]];
+      const int next = s + 1 < n - 1 ? dorder[s + 1] : -1;
+      int sp = 0xff, sa = 0xff, sb = 0xff, flags = 0;
+      if (v == root) {
+        // pre[root] = pi
+      } else if (s > 0 && parent[v] == dorder[s - 1]) {
+        flags |= 8;  // carried in registers from the previous step
+      } else {
+        sp = slot_of[v];
+        pool.release(sp);
+      }
+      const int ch[2] = {a, b};
+      int* sl[2] = {&sa, &sb};
+      for (int k = 0; k < 2; ++k) {
+        const int c = ch[k];
+        if (!internal(c)) {
+          flags |= 1 << k;
+        } else {
+          msg_rows[nmsg++] = up_row[c];
+          if (c != next) {
+            *sl[k] = pool.alloc();  // parked until the DFS returns to it
+            slot_of[c] = *sl[k];
+            flags |= 0x20 << k;
+            if (*sl[k] >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
+          }
+        }
+      }
+      down[s] = Op{a | (b << 16), v, sp | (sa << 8) | (sb << 16), flags};
+      down_nodes[2 * s] = a;
+      down_nodes[2 * s + 1] = b;
+    }
     msg_start[(n - 1 + kChunkSteps - 1) / kChunkSteps] = nmsg;
     *depth_down = std::max(pool.high, 1);
   }

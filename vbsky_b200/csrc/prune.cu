@@ -186,6 +186,13 @@ __device__ __forceinline__ void store_rows(double* base, const double (&x)[NS][4
   for (int i = 0; i < 4; ++i) *reinterpret_cast<double2*>(base + i * TILE) = make_double2(x[0][i], x[1][i]);
 }
 
+__device__ __forceinline__ void copy_rows(const double (&src)[NS][4], double (&dst)[NS][4]) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[s][i] = src[s][i];
+}
+
 struct RingState {
   uint32_t cst = 0, cph = 0;  // step-chunk ring stage / phase
   uint32_t mst = 0, mph = 0;  // message ring slot / phase
@@ -241,6 +248,7 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
   double sc[NS] = {1.0, 1.0};
   int ex[NS] = {0, 0};
   double ll_site[NS] = {0.0, 0.0};
+  double carry[NS][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};  // result of the previous step
   for (int c0 = 0; c0 < nsteps; c0 += CH) {
     const unsigned char* stage = smem + OFF_STAGE + rs.cst * STAGE_BYTES;
     mbar_wait(bar_full_c(bars, rs.cst), rs.cph);
@@ -252,10 +260,14 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
       double ma[NS][4], mb[NS][4], dummy[NS][4];
       if (op.w & 1)
         tip_messages<CLIP, false>(rec + UP_A, nullptr, crow, ma, dummy);
+      else if (op.w & 8)
+        copy_rows(carry, ma);
       else
         load_rows(stk + (op.z & 0xff) * (4 * TILE) + NS * tid, ma);
       if (op.w & 2)
         tip_messages<CLIP, false>(rec + UP_B, nullptr, crow + CODE_ROW, mb, dummy);
+      else if (op.w & 16)
+        copy_rows(carry, mb);
       else
         load_rows(stk + ((op.z >> 8) & 0xff) * (4 * TILE) + NS * tid, mb);
       double pr[NS][4];
@@ -298,7 +310,8 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             v[s][i] = clipv<CLIP>(M[i * 4 + 0] * post[s][0] + M[i * 4 + 1] * post[s][1] + M[i * 4 + 2] * post[s][2] + M[i * 4 + 3] * post[s][3]);
-        store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, v);
+        copy_rows(v, carry);
+        if (op.w & 32) store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, v);  // parked for a later step
         if (WANT_GRAD) {
           double* gdst = myscr + (size_t)(c0 + k) * (4 * TILE);
 #pragma unroll
@@ -351,7 +364,9 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
       const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + NS * tid;
       const int sp = op.z & 0xff;
       double pre[NS][4];
-      if (sp == 0xff) {
+      if (op.w & 8) {
+        copy_rows(carry, pre);  // computed by the previous step
+      } else if (sp == 0xff) {
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -425,7 +440,10 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
             for (int v = 0; v < 4; ++v) B[s][v] = scale_pow2(B[s][v], ed[s]);
           }
         }
-        store_rows(stk + ((op.z >> 8) & 0xff) * (4 * TILE) + NS * tid, B);
+        if (op.w & 32)
+          store_rows(stk + ((op.z >> 8) & 0xff) * (4 * TILE) + NS * tid, B);  // parked until the walk returns to it
+        else
+          copy_rows(B, carry);  // child a is expanded by the next step
       }
       if (!(op.w & 2)) {
         double M[16];
@@ -445,7 +463,10 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
             for (int v = 0; v < 4; ++v) B[s][v] = scale_pow2(B[s][v], ed[s]);
           }
         }
-        store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, B);
+        if (op.w & 64)
+          store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, B);
+        else
+          copy_rows(B, carry);
       }
 
       if (gslot + 2 == GCH || step == nsteps - 1) {
