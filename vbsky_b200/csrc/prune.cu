@@ -45,7 +45,7 @@ constexpr int NCW = CT / 32;          // consumer warps
 constexpr int THREADS = CT + 32;      // + producer warp
 constexpr int CH = kChunkSteps;       // steps per ring stage
 constexpr int NST = 2;                // step-chunk ring stages
-constexpr int NMS = 2;                // message ring slots
+constexpr int NMS_MAX = 2;            // message ring slots (a deeper ring measured slower: it only shrinks L1)
 constexpr int TIPM = 20;              // doubles of a tip-branch table: columns of P(t) for A,C,G,T and their sum (N)
 constexpr int UPREC = 2 + 2 * TIPM + 16;  // up-step record:   op(2) Ta(20) Tb(20) Pp(16)
 constexpr int DNREC = 2 + 4 * TIPM;       // down-step record: op(2) Ta|Pa(20) Tb|Pb(20) QTa(20) QTb(20)
@@ -59,7 +59,7 @@ constexpr int GCH = 8;                // branch gradients staged per reduction r
 constexpr int GROW = CT + 1;          // one staged value per consumer thread (its two sites pre-added)
 constexpr int OFF_STAGE = 128;
 constexpr int OFF_MSG = OFF_STAGE + ((NST * STAGE_BYTES + 127) / 128) * 128;
-constexpr int OFF_STK = OFF_MSG + NMS * MSG_BYTES;
+
 static_assert(NS == 2, "the consumer code is written for two sites per thread");
 static_assert(STAGE_BYTES % 16 == 0 && (UPREC * 8) % 16 == 0 && (DNREC * 8) % 16 == 0, "bulk copies need 16-byte granularity");
 static_assert(CT % GCH == 0 && GCH % 2 == 0, "gradient staging geometry");
@@ -80,7 +80,7 @@ struct PruneParams {
   double* g_part;            // [U][tiles][2n-2]
   double Q[16];
   double pi[4];
-  int n, U, tiles, depth;
+  int n, U, tiles, depth, nms;
   long long S, S_pad;
 };
 
@@ -199,8 +199,8 @@ struct RingState {
   __device__ __forceinline__ void adv_c() {
     if (++cst == NST) cst = 0, cph ^= 1;
   }
-  __device__ __forceinline__ void adv_m() {
-    if (++mst == NMS) mst = 0, mph ^= 1;
+  __device__ __forceinline__ void adv_m(uint32_t nms) {
+    if (++mst == nms) mst = 0, mph ^= 1;
   }
 };
 
@@ -208,8 +208,8 @@ struct RingState {
 __device__ __forceinline__ uint32_t bar_full_c(uint32_t base, uint32_t s) { return base + 8 * s; }
 __device__ __forceinline__ uint32_t bar_empty_c(uint32_t base, uint32_t s) { return base + 8 * (NST + s); }
 __device__ __forceinline__ uint32_t bar_full_m(uint32_t base, uint32_t s) { return base + 8 * (2 * NST + s); }
-__device__ __forceinline__ uint32_t bar_empty_m(uint32_t base, uint32_t s) { return base + 8 * (2 * NST + NMS + s); }
-__device__ __forceinline__ uint32_t bar_up_done(uint32_t base) { return base + 8 * (2 * NST + 2 * NMS); }
+__device__ __forceinline__ uint32_t bar_empty_m(uint32_t base, uint32_t s) { return base + 8 * (2 * NST + NMS_MAX + s); }
+__device__ __forceinline__ uint32_t bar_up_done(uint32_t base) { return base + 8 * (2 * NST + 2 * NMS_MAX); }
 
 // Message of a tip child for this thread's two sites (+ optionally Q P(t) e_mask for the gradient).
 template <bool CLIP, bool WITH_Q>
@@ -233,7 +233,7 @@ template <bool WANT_GRAD, bool CLIP>
 __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char* smem, RingState& rs, int u, int tile,
                                              int t, double* myscr) {
   const uint32_t bars = smem_u32(smem);
-  double* stk = reinterpret_cast<double*>(smem + OFF_STK);  // [depth][4][TILE]
+  double* stk = reinterpret_cast<double*>(smem + OFF_MSG + p.nms * MSG_BYTES);  // [depth][4][TILE]
   double* gst = stk + (size_t)p.depth * 4 * TILE;           // [GCH][GROW]
   double* red = gst + GCH * GROW;                           // [CT]
   const int tid = threadIdx.x;
@@ -382,7 +382,7 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
         load_rows(reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + NS * tid, ma);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty_m(bars, rs.mst));
-        rs.adv_m();
+        rs.adv_m(p.nms);
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -396,7 +396,7 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
         load_rows(reinterpret_cast<const double*>(smem + OFF_MSG + rs.mst * MSG_BYTES) + NS * tid, mb);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty_m(bars, rs.mst));
-        rs.adv_m();
+        rs.adv_m(p.nms);
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) 
   const long long items = (long long)p.U * p.tiles;
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) mbar_init(bar_full_c(bars, i), 1), mbar_init(bar_empty_c(bars, i), NCW);
-    for (int i = 0; i < NMS; ++i) mbar_init(bar_full_m(bars, i), 1), mbar_init(bar_empty_m(bars, i), NCW);
+    for (int i = 0; i < NMS_MAX; ++i) mbar_init(bar_full_m(bars, i), 1), mbar_init(bar_empty_m(bars, i), NCW);
     mbar_init(bar_up_done(bars), NCW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(THREADS, 3) prune_kernel(const PruneParams p) 
           const uint32_t mfull = bar_full_m(bars, rs.mst);
           mbar_expect_tx(mfull, MSG_BYTES);
           bulk_g2s(smem_u32(smem + OFF_MSG + rs.mst * MSG_BYTES), scr_base + (size_t)row * MSG_BYTES, MSG_BYTES, mfull);
-          rs.adv_m();
+          rs.adv_m(p.nms);
         }
       }
     }
@@ -686,7 +686,7 @@ __global__ void finalize_kernel(const double* __restrict__ ll_part, const double
 }
 
 struct PruneConfig {
-  int grid = 0, depth = 0, tiles = 0;
+  int grid = 0, depth = 0, tiles = 0, nms = 2;
   size_t smem = 0;
   size_t off_uptab = 0, off_dntab = 0, off_flags = 0, off_scratch = 0, off_llpart = 0, off_gpart = 0, total = 0;
 };
@@ -704,27 +704,47 @@ static thread_local TimingState g_timing;
 static int prune_config(const vbsky_layout* lay, const vbsky_tips* tips, int U, bool want_grad, PruneConfig* cfg) {
   const int n = lay->n;
   cfg->depth = want_grad ? std::max(lay->depth_up, lay->depth_down) : lay->depth_up;
-  cfg->smem = (size_t)OFF_STK + ((size_t)cfg->depth * 4 * TILE + (size_t)GCH * GROW + TILE) * sizeof(double);
   cfg->tiles = tips->tiles;
   int dev = 0, sms = 0, per_sm = 0, max_smem = 0;
   VB_CUDA(cudaGetDevice(&dev));
   VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   VB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (cfg->smem > (size_t)max_smem)
-    return set_error(VBSKY_EINVAL, "tree needs %d live vectors (%zu B shared memory) but the device offers %d B", cfg->depth, cfg->smem, max_smem);
-  int per_sm2 = 0;
-  if (want_grad) {
-    VB_CUDA(cudaFuncSetAttribute(prune_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaFuncSetAttribute(prune_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<true, false>, THREADS, cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, prune_kernel<true, true>, THREADS, cfg->smem));
-  } else {
-    VB_CUDA(cudaFuncSetAttribute(prune_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaFuncSetAttribute(prune_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<false, false>, THREADS, cfg->smem));
-    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, prune_kernel<false, true>, THREADS, cfg->smem));
+  auto smem_for = [&](int nms) {
+    return (size_t)OFF_MSG + (size_t)nms * MSG_BYTES + ((size_t)cfg->depth * 4 * TILE + (size_t)GCH * GROW + TILE) * sizeof(double);
+  };
+  if (smem_for(2) > (size_t)max_smem)
+    return set_error(VBSKY_EINVAL, "tree needs %d parked vectors (%zu B shared memory) but the device offers %d B", cfg->depth, smem_for(2), max_smem);
+  auto occupancy = [&](size_t smem, int* out) -> int {
+    int a = 0, b = 0;
+    if (want_grad) {
+      VB_CUDA(cudaFuncSetAttribute(prune_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VB_CUDA(cudaFuncSetAttribute(prune_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, prune_kernel<true, false>, THREADS, smem));
+      VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, prune_kernel<true, true>, THREADS, smem));
+    } else {
+      VB_CUDA(cudaFuncSetAttribute(prune_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VB_CUDA(cudaFuncSetAttribute(prune_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, prune_kernel<false, false>, THREADS, smem));
+      VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, prune_kernel<false, true>, THREADS, smem));
+    }
+    *out = std::min(a, b);
+    return VBSKY_OK;
+  };
+  // deepest message ring that does not cost a resident CTA
+  int rc = occupancy(smem_for(2), &per_sm);
+  if (rc != VBSKY_OK) return rc;
+  cfg->nms = 2;
+  for (int nms = 3; nms <= NMS_MAX; ++nms) {
+    int occ = 0;
+    if (smem_for(nms) > (size_t)max_smem) break;
+    rc = occupancy(smem_for(nms), &occ);
+    if (rc != VBSKY_OK) return rc;
+    if (occ < per_sm) break;
+    cfg->nms = nms;
   }
-  per_sm = std::min(per_sm, per_sm2);
+  cfg->smem = smem_for(cfg->nms);
+  rc = occupancy(cfg->smem, &per_sm);  // leaves the function attributes at the chosen size
+  if (rc != VBSKY_OK) return rc;
   if (per_sm < 1) return set_error(VBSKY_ECUDA, "pruning kernel cannot be resident (smem %zu B)", cfg->smem);
   const long long items = (long long)U * cfg->tiles;
   const long long slots = (long long)sms * per_sm;
@@ -796,7 +816,7 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
   p.g_part = (double*)(base + cfg.off_gpart);
   vbsky_subst_rate_matrix(model, p.Q);
   for (int i = 0; i < 4; ++i) p.pi[i] = model->pi[i];
-  p.n = n, p.U = U, p.tiles = cfg.tiles, p.depth = cfg.depth;
+  p.n = n, p.U = U, p.tiles = cfg.tiles, p.depth = cfg.depth, p.nms = cfg.nms;
   p.S = tips->S, p.S_pad = tips->S_pad;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_timing.enabled) {
