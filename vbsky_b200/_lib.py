@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvbsky_b200.so")
+LIB_PATH = os.environ.get("VBSKY_B200_LIB") or os.path.join(_HERE, "libvbsky_b200.so")  # env override: A/B builds
 
 
 class VbskyError(RuntimeError):

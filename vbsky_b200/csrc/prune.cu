@@ -56,13 +56,13 @@ constexpr int STAGE_BYTES = CH * DNREC * 8 + 2 * CH * CODE_ROW;
 constexpr int STAGE_CODES = CH * DNREC * 8;  // byte offset of the code rows inside a stage
 constexpr int MSG_BYTES = 4 * TILE * 8;
 constexpr int GCH = 8;                // branch gradients staged per reduction round
-constexpr int GROW = CT + 1;          // one staged value per consumer thread (its two sites pre-added)
+constexpr int GROW = 33;              // per-warp staging row: one value per lane (its two sites pre-added) + pad
 constexpr int OFF_STAGE = 128;
 constexpr int OFF_MSG = OFF_STAGE + ((NST * STAGE_BYTES + 127) / 128) * 128;
 
 static_assert(NS == 2, "the consumer code is written for two sites per thread");
 static_assert(STAGE_BYTES % 16 == 0 && (UPREC * 8) % 16 == 0 && (DNREC * 8) % 16 == 0, "bulk copies need 16-byte granularity");
-static_assert(CT % GCH == 0 && GCH % 2 == 0, "gradient staging geometry");
+static_assert(GCH == 8, "the per-warp gradient reduction assumes 8 staged branches x 4 lane groups");
 
 struct PruneParams {
   const double* uptab;    // [U][n-1][UPREC]
@@ -120,7 +120,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
 template <bool CLIP>
 __device__ __forceinline__ double clipv(double x) {
@@ -234,8 +233,7 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
                                              int t, double* myscr) {
   const uint32_t bars = smem_u32(smem);
   double* stk = reinterpret_cast<double*>(smem + OFF_MSG + p.nms * MSG_BYTES);  // [depth][4][TILE]
-  double* gst = stk + (size_t)p.depth * 4 * TILE;           // [GCH][GROW]
-  double* red = gst + GCH * GROW;                           // [CT]
+  double* gst = stk + (size_t)p.depth * 4 * TILE;           // [NCW][GCH][GROW]
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int n = p.n;
@@ -339,20 +337,13 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
     double v = cnt[0] * ll_site[0] + cnt[1] * ll_site[1];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    consumer_bar();
-    if (lane == 0) red[tid >> 5] = v;
-    consumer_bar();
-    if (tid == 0) {
-      double tot = 0.0;
-#pragma unroll
-      for (int w = 0; w < NCW; ++w) tot += red[w];
-      p.ll_part[(size_t)u * p.tiles + tile] = tot;
-    }
+    if (lane == 0) p.ll_part[((size_t)u * p.tiles + tile) * NCW + (tid >> 5)] = v;  // per-warp partial
   }
   if (!WANT_GRAD) return;
 
   // ------------------------------------------- down pass (prune.py:52-96) + eq. (9) (prune.py:146)
-  double* gout = p.g_part + ((size_t)u * p.tiles + tile) * (2 * n - 2);
+  double* gout = p.g_part + (((size_t)u * p.tiles + tile) * NCW + (tid >> 5)) * (2 * n - 2);  // this warp's partials
+  double* gstw = gst + (tid >> 5) * (GCH * GROW);
   for (int c0 = 0; c0 < nsteps; c0 += CH) {
     const unsigned char* stage = smem + OFF_STAGE + rs.cst * STAGE_BYTES;
     mbar_wait(bar_full_c(bars, rs.cst), rs.cph);
@@ -418,8 +409,8 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
         const double gb = ((wb[s][0] * qb[s][0] + wb[s][1] * qb[s][1]) + (wb[s][2] * qb[s][2] + wb[s][3] * qb[s][3])) * rden;
         gsum_a += ga, gsum_b += gb;
       }
-      gst[gslot * GROW + tid] = gsum_a;
-      gst[(gslot + 1) * GROW + tid] = gsum_b;
+      gstw[gslot * GROW + lane] = gsum_a;
+      gstw[(gslot + 1) * GROW + lane] = gsum_b;
 
       if (!(op.w & 1)) {
         double M[16];
@@ -470,32 +461,25 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
       }
 
       if (gslot + 2 == GCH || step == nsteps - 1) {
-        // transposed reduction of the staged round over the tile's sites
+        // transposed reduction of the staged round over the warp's 64 sites: lane (r, q) adds 8 lanes' values
+        // of branch r, two shuffles fold the four q groups; no CTA-wide barrier anywhere in the walk
         const int nval = gslot + 2;
-        consumer_bar();
-        const int r = tid & (GCH - 1), q = tid / GCH;  // CT/GCH column groups of GCH threads' values
-        constexpr int COLS = GCH;
+        __syncwarp();
+        const int r = lane & (GCH - 1), q = lane / GCH;
+        const double* row = gstw + r * GROW + q * GCH;
         double acc = 0.0;
-        if (r < nval) {
-          const double* row = gst + r * GROW + q * COLS;
 #pragma unroll
-          for (int kk = 0; kk < COLS; ++kk) acc += row[kk];
-        }
-        red[q * GCH + r] = acc;
-        consumer_bar();
-        if (tid < nval) {
-          double tot = 0.0;
-#pragma unroll
-          for (int kk = 0; kk < CT / GCH; ++kk) tot += red[kk * GCH + tid];
-          gout[2 * step + 2 - nval + tid] = tot;
-        }
+        for (int kk = 0; kk < GCH; ++kk) acc += row[kk];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (lane < nval) gout[2 * step + 2 - nval + lane] = acc;
+        __syncwarp();
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty_c(bars, rs.cst));
     rs.adv_c();
   }
-  consumer_bar();  // red / gst are reused by the next item
 }
 
 // Each launch handles the units whose clip flag equals CLIP and skips the others (two launches per
@@ -710,7 +694,7 @@ static int prune_config(const vbsky_layout* lay, const vbsky_tips* tips, int U, 
   VB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   VB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   auto smem_for = [&](int nms) {
-    return (size_t)OFF_MSG + (size_t)nms * MSG_BYTES + ((size_t)cfg->depth * 4 * TILE + (size_t)GCH * GROW + TILE) * sizeof(double);
+    return (size_t)OFF_MSG + (size_t)nms * MSG_BYTES + ((size_t)cfg->depth * 4 * TILE + (size_t)NCW * GCH * GROW) * sizeof(double);
   };
   if (smem_for(2) > (size_t)max_smem)
     return set_error(VBSKY_EINVAL, "tree needs %d parked vectors (%zu B shared memory) but the device offers %d B", cfg->depth, smem_for(2), max_smem);
@@ -755,8 +739,8 @@ static int prune_config(const vbsky_layout* lay, const vbsky_tips* tips, int U, 
   cfg->off_dntab = off, off = align(off + (want_grad ? (size_t)U * (n - 1) * DNREC * sizeof(double) : 0));
   cfg->off_flags = off, off = align(off + (size_t)U * sizeof(uint32_t));
   cfg->off_scratch = off, off = align(off + (want_grad ? (size_t)slots * (n - 1) * MSG_BYTES : 0));
-  cfg->off_llpart = off, off = align(off + (size_t)U * cfg->tiles * sizeof(double));
-  cfg->off_gpart = off, off = align(off + (want_grad ? (size_t)U * cfg->tiles * (2 * n - 2) * sizeof(double) : 0));
+  cfg->off_llpart = off, off = align(off + (size_t)U * cfg->tiles * NCW * sizeof(double));
+  cfg->off_gpart = off, off = align(off + (want_grad ? (size_t)U * cfg->tiles * NCW * (2 * n - 2) * sizeof(double) : 0));
   cfg->total = off;
   return VBSKY_OK;
 }
@@ -841,7 +825,7 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
   VB_CUDA(cudaGetLastError());
   {
     dim3 grid((unsigned)U, (unsigned)((2 * n - 2 + 127) / 128));
-    finalize_kernel<<<grid, 128, 0, stream>>>(p.ll_part, p.g_part, unit_tree, lay->d_down_nodes, U, n, cfg.tiles, ll, dll_dbl);
+    finalize_kernel<<<grid, 128, 0, stream>>>(p.ll_part, p.g_part, unit_tree, lay->d_down_nodes, U, n, cfg.tiles * NCW, ll, dll_dbl);
     VB_CUDA(cudaGetLastError());
   }
   g_stats[0] = 4, g_stats[1] = cfg.grid, g_stats[2] = TILE, g_stats[3] = (int64_t)cfg.smem;
@@ -851,7 +835,7 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
     // partials out.  The per-unit step tables are L2-resident across a unit's tiles and not counted.
     const double S = (double)tips->S;
     double bytes = (double)U * S * n * (want_grad ? 2.0 : 1.0) + (double)U * S * 8.0 + (site_ll ? (double)U * S * 8.0 : 0.0);
-    if (want_grad) bytes += (double)U * S * (n - 2) * 32.0 * 2.0 + (double)U * cfg.tiles * (2.0 * n - 2) * 8.0;
+    if (want_grad) bytes += (double)U * S * (n - 2) * 32.0 * 2.0 + (double)U * cfg.tiles * NCW * (2.0 * n - 2) * 8.0;
     g_stats[4] = (int64_t)bytes;
   }
   return VBSKY_OK;
