@@ -154,7 +154,8 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
         a, b = x & 0xFFFF, (x >> 16) & 0xFFFF
         assert bool(w & 1) == (a < n) and bool(w & 2) == (b < n) and bool(w & 4) == (par == root)
         ma = Q.expm_action(bl[a], partials[:, a]) if w & 1 else (carry.copy() if w & 8 else stack[z & 0xFF].copy())
-        mb = Q.expm_action(bl[b], partials[:, b]) if w & 2 else (carry.copy() if w & 16 else stack[(z >> 8) & 0xFF].copy())
+        assert not (w & 16), "only child a is ever the carried result"
+        mb = Q.expm_action(bl[b], partials[:, b]) if w & 2 else stack[(z >> 8) & 0xFF].copy()
         assert not np.isnan(ma).any() and not np.isnan(mb).any()
         pr = ma * mb
         if w & 4:
@@ -188,19 +189,11 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
         g[:, b] = (wb * qb).sum(1) / den
         if not (w & 1):
             B = Q.expm_action(bl[a], wa, right=False)
-            B = B / B.sum(1, keepdims=True)
-            if w & 32:
-                stack[(z >> 8) & 0xFF] = B
-            else:
-                carry = B
+            carry = B / B.sum(1, keepdims=True)  # an internal a is expanded by the next step
+            assert step + 1 < len(down) and down[step + 1][1] == a
         if not (w & 2):
             B = Q.expm_action(bl[b], wb, right=False)
-            B = B / B.sum(1, keepdims=True)
-            if w & 64:
-                stack[(z >> 16) & 0xFF] = B
-            else:
-                assert w & 32 or (w & 1), "only one child's pre vector can be carried"
-                carry = B
+            stack[(z >> 16) & 0xFF] = B / B.sum(1, keepdims=True)  # an internal b is parked
     return ll, g
 
 

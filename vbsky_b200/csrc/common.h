@@ -29,13 +29,14 @@ int set_error(int code, const char* fmt, ...);
 
 // One step of the up (postorder) pass: combine children a and b into parent p.
 //   x = a | b<<16, y = p, z = slotA | slotB<<8 | slotOut<<16 (shared-memory slots; 0xff = none),
-//   w = flags: bit0 a is a tip, bit1 b is a tip, bit2 p is the root, bit3 / bit4 a / b is the result of the
-//   previous step (still in registers), bit5 the result must also be parked in slotOut.
-//   The message produced by step s is streamed to scratch row s.
+//   w = flags: bit0 a is a tip, bit1 b is a tip, bit2 p is the root, bit3 a is the result of the previous
+//   step (still in registers; the children are ordered so that only a ever is), bit5 the result must
+//   also be parked in slotOut.  The message produced by step s is streamed to scratch row s.
 // One step of the down (preorder) pass: expand parent p into children a and b.
-//   x = a | b<<16, y = p, z = slotP | slotA<<8 | slotB<<16, w = flags: bit0/bit1 tips as above,
-//   bit3 pre_p is carried in registers from the previous step (else slotP, or pi for the root),
-//   bit5 / bit6 pre_a / pre_b is parked in its slot (else carried into the next step).
+//   x = a | b<<16, y = p, z = slotP | 0xff<<8 | slotB<<16, w = flags: bit0/bit1 tips as above,
+//   bit3 pre_p is carried in registers from the previous step (else slotP, or pi for the root).
+//   The children are ordered so that an internal a is expanded by the next step (its pre vector is
+//   carried) and an internal b is parked in slotB until the walk returns to it.
 //   Internal children's messages arrive through the message ring in the order a, b (h_msg_rows).
 struct Op {
   int32_t x, y, z, w;

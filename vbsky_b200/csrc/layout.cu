@@ -104,20 +104,27 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
     for (int s = 0; s < n - 1; ++s) {
       const int v = order[s];
       const int a = pc[2 * v + first[v]], b = pc[2 * v + 1 - first[v]];
-      int sa = 0xff, sb = 0xff, so = 0xff, flags = 0;
-      const int ch[2] = {a, b};
-      int* sl[2] = {&sa, &sb};
+      int so = 0xff, flags = 0;
+      // source of each child's message: 0 tip, 1 previous step's result (registers), 2 parked in a slot
+      int ch[2] = {a, b}, src[2] = {0, 0}, slot[2] = {0xff, 0xff};
       for (int k = 0; k < 2; ++k) {
         const int c = ch[k];
         if (!internal(c)) {
-          flags |= 1 << k;  // tip
+          src[k] = 0;
         } else if (up_row[c] == s - 1) {
-          flags |= 8 << k;  // result of the previous step, still in registers
+          src[k] = 1;
         } else {
-          *sl[k] = slot_of[c];
+          src[k] = 2;
+          slot[k] = slot_of[c];
           pool.release(slot_of[c]);
         }
       }
+      if (src[1] == 1) std::swap(ch[0], ch[1]), std::swap(src[0], src[1]), std::swap(slot[0], slot[1]);  // canonical: only a is ever carried
+      for (int k = 0; k < 2; ++k) {
+        if (src[k] == 0) flags |= 1 << k;
+        if (src[k] == 1) flags |= 8 << k;
+      }
+      const int ca = ch[0], cb = ch[1], sa = slot[0], sb = slot[1];
       if (v == root) {
         flags |= 4;
       } else if (up_row[parent[v]] != s + 1) {
@@ -126,7 +133,7 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
         flags |= 0x20;
         if (so >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
       }
-      up[s] = Op{a | (b << 16), v, sa | (sb << 8) | (so << 16), flags};
+      up[s] = Op{ca | (cb << 16), v, sa | (sb << 8) | (so << 16), flags};
     }
     *depth_up = std::max(pool.high, 1);
   }
@@ -174,7 +181,8 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
     for (int s = 0; s < n - 1; ++s) {
       const int v = dorder[s];
       if (s % kChunkSteps == 0) msg_start[s / kChunkSteps] = nmsg;
-      const int a = pc[2 * v + firstd[v]], b = pc[2 * v + 1 - firstd[v]];
+      int a = pc[2 * v + firstd[v]], b = pc[2 * v + 1 - firstd[v]];
+      if (!internal(a) && internal(b)) std::swap(a, b);  // canonical: an internal a is expanded next (carried), an internal b is parked
       const int next = s + 1 < n - 1 ? dorder[s + 1] : -1;
       int sp = 0xff, sa = 0xff, sb = 0xff, flags = 0;
       if (v == root) {
@@ -185,21 +193,16 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
         sp = slot_of[v];
         pool.release(sp);
       }
-      const int ch[2] = {a, b};
-      int* sl[2] = {&sa, &sb};
-      for (int k = 0; k < 2; ++k) {
-        const int c = ch[k];
-        if (!internal(c)) {
-          flags |= 1 << k;
-        } else {
-          msg_rows[nmsg++] = up_row[c];
-          if (c != next) {
-            *sl[k] = pool.alloc();  // parked until the DFS returns to it
-            slot_of[c] = *sl[k];
-            flags |= 0x20 << k;
-            if (*sl[k] >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
-          }
-        }
+      if (internal(a) && a != next) return set_error(VBSKY_EINVAL, "internal error: down schedule order");
+      if (!internal(a)) flags |= 1;
+      else msg_rows[nmsg++] = up_row[a];
+      if (!internal(b)) {
+        flags |= 2;
+      } else {
+        msg_rows[nmsg++] = up_row[b];
+        sb = pool.alloc();  // parked until the walk returns to it
+        slot_of[b] = sb;
+        if (sb >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
       }
       down[s] = Op{a | (b << 16), v, sp | (sa << 8) | (sb << 16), flags};
       down_nodes[2 * s] = a;

@@ -255,17 +255,14 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
       const double* rec = reinterpret_cast<const double*>(stage) + k * UPREC;
       const int4 op = *reinterpret_cast<const int4*>(rec);
       const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + NS * tid;
-      double ma[NS][4], mb[NS][4], dummy[NS][4];
+      double (&ma)[NS][4] = carry;  // child a: already there when it is the previous step's result
+      double mb[NS][4], dummy[NS][4];
       if (op.w & 1)
         tip_messages<CLIP, false>(rec + UP_A, nullptr, crow, ma, dummy);
-      else if (op.w & 8)
-        copy_rows(carry, ma);
-      else
+      else if (!(op.w & 8))
         load_rows(stk + (op.z & 0xff) * (4 * TILE) + NS * tid, ma);
       if (op.w & 2)
         tip_messages<CLIP, false>(rec + UP_B, nullptr, crow + CODE_ROW, mb, dummy);
-      else if (op.w & 16)
-        copy_rows(carry, mb);
       else
         load_rows(stk + ((op.z >> 8) & 0xff) * (4 * TILE) + NS * tid, mb);
       double pr[NS][4];
@@ -294,10 +291,16 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
 #pragma unroll
             for (int i = 0; i < 4; ++i) post[s][i] = pr[s][i] * inv;
           } else {
-            const int e = exponent_of(c);  // rescale by 2^-e: exact, sum ends up in [1, 2)
-            ex[s] += e;
+            // messages stay unnormalised; only when the magnitude has drifted below 2^-256 is it pulled back
+            // by an exact power of two (a step shrinks it by at most ~2^-133, so nothing underflows)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) post[s][i] = scale_pow2(pr[s][i], e);
+            for (int i = 0; i < 4; ++i) post[s][i] = pr[s][i];
+            if (__double2hiint(c) < ((1023 - 256) << 20)) {
+              const int e = exponent_of(c);
+              ex[s] += e;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) post[s][i] = scale_pow2(pr[s][i], e);
+            }
           }
         }
         double M[16];
@@ -308,7 +311,7 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             v[s][i] = clipv<CLIP>(M[i * 4 + 0] * post[s][0] + M[i * 4 + 1] * post[s][1] + M[i * 4 + 2] * post[s][2] + M[i * 4 + 3] * post[s][3]);
-        copy_rows(v, carry);
+        copy_rows(v, carry);  // the next step's child a, if it consumes this result
         if (op.w & 32) store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, v);  // parked for a later step
         if (WANT_GRAD) {
           double* gdst = myscr + (size_t)(c0 + k) * (4 * TILE);
@@ -354,9 +357,8 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
       const int4 op = *reinterpret_cast<const int4*>(rec);
       const unsigned char* crow = stage + STAGE_CODES + 2 * k * CODE_ROW + NS * tid;
       const int sp = op.z & 0xff;
-      double pre[NS][4];
+      double (&pre)[NS][4] = carry;  // already there when the previous step computed it
       if (op.w & 8) {
-        copy_rows(carry, pre);  // computed by the previous step
       } else if (sp == 0xff) {
 #pragma unroll
         for (int s = 0; s < NS; ++s)
@@ -425,16 +427,13 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
             const double inv = 1.0 / ((B[s][0] + B[s][1]) + (B[s][2] + B[s][3]));  // B /= c (prune.py:74)
 #pragma unroll
             for (int v = 0; v < 4; ++v) B[s][v] *= inv;
-          } else {
-            // any positive rescaling cancels in g = num/den; 2^-exponent(den) keeps pre within ~[1, 1e20]
+          } else if (ed[s] < -400) {
+            // any positive rescaling cancels in g = num/den: pull pre back by 2^-exponent(den) only when it has drifted far
 #pragma unroll
             for (int v = 0; v < 4; ++v) B[s][v] = scale_pow2(B[s][v], ed[s]);
           }
         }
-        if (op.w & 32)
-          store_rows(stk + ((op.z >> 8) & 0xff) * (4 * TILE) + NS * tid, B);  // parked until the walk returns to it
-        else
-          copy_rows(B, carry);  // child a is expanded by the next step
+        copy_rows(B, carry);  // an internal child a is always expanded by the next step
       }
       if (!(op.w & 2)) {
         double M[16];
@@ -449,15 +448,12 @@ __device__ __forceinline__ void consume_item(const PruneParams& p, unsigned char
             const double inv = 1.0 / ((B[s][0] + B[s][1]) + (B[s][2] + B[s][3]));
 #pragma unroll
             for (int v = 0; v < 4; ++v) B[s][v] *= inv;
-          } else {
+          } else if (ed[s] < -400) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) B[s][v] = scale_pow2(B[s][v], ed[s]);
           }
         }
-        if (op.w & 64)
-          store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, B);
-        else
-          copy_rows(B, carry);
+        store_rows(stk + ((op.z >> 16) & 0xff) * (4 * TILE) + NS * tid, B);  // an internal child b is parked until the walk returns to it
       }
 
       if (gslot + 2 == GCH || step == nsteps - 1) {
