@@ -33,6 +33,7 @@ WORKLOADS = {
 }
 KAPPA = 2.7
 M_INTERVALS = 50  # skyline intervals (paper/covid.py m=50)
+NCU_DRAM_BYTES_CONFIG3 = 203.299431e9 + 191.150824e9
 UNIT = "ELBO+grad evals/s"
 METRIC = "elbo_grad_evals_per_sec"
 
@@ -303,7 +304,10 @@ def main():
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "kernel": "prune_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+            "frac": achieved / peak, "peak_source": peak_src,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r1_prune_kernel_bench_ncu_summary.txt
+            # (one ncu --set full capture of this workload on one GPU); null for any other workload
+            "traffic": NCU_DRAM_BYTES_CONFIG3 if (args.workload == "config3" and world == 1 and not args.trees) else None,
             "algorithmic_bytes_per_launch": stats["algorithmic_bytes"], "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
         },
     }
