@@ -217,6 +217,22 @@ int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips,
                                 double* ll_tree, double* ll_data, vbsky_param_grads* grads,
                                 void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Local variational family (the per-tree flows of fasta.py:378-384): reparameterised samples
+ *   x = clip(expit(mu + exp(log_sigma) * eps), 1e-7, 1-1e-7)
+ * (Transform(dim, Compose(DiagonalAffine, ZeroOne)) over MeanField: prob/transform.py:130-202,
+ * prob/distribution.py:52-65) and log q(x) as TransformedDistribution.log_pdf computes it
+ * (transform.py:56-63), for the entropy term of optim.loss (optim.py:54-65).
+ * mu, log_sigma dev [T][d] per tree; eps dev [U][d] standard-normal base draws (supplied by the
+ * caller); x dev [U][d]; logq dev [U].  backward: given dx [U][d] and dlogq [U] (either may be NULL)
+ * writes the per-unit adjoints dmu, dlog_sigma [U][d] (the caller sums the units of a tree).     */
+int vbsky_local_flow_sample(int32_t U, int32_t d, const int32_t* unit_tree, const double* mu,
+                            const double* log_sigma, const double* eps, double* x, double* logq,
+                            void* stream);
+int vbsky_local_flow_backward(int32_t U, int32_t d, const int32_t* unit_tree, const double* mu,
+                              const double* log_sigma, const double* eps, const double* dx,
+                              const double* dlogq, double* dmu, double* dlog_sigma, void* stream);
+
 /* CUDA-event timing of the fused pruning kernel alone (used for the roofline figure): after
  * vbsky_prune_timing(1, NULL, NULL) every prune call of this thread brackets the kernel with an
  * event pair on its stream; a later call drains them into *ms_sum / *launches (and sets the new

@@ -132,3 +132,20 @@ def test_bdsky_oracle_gradients_match_finite_differences():
                 p[k][i] = o
             fd = (lp - lm) / (2 * eps)
             assert abs(fd - p[k].grad[i].item()) <= 1e-6 * max(1.0, abs(fd)), (k, i)
+
+
+def test_local_flow_oracle_change_of_variables():
+    """prob/transform.py restatement: away from the ZeroOne clip, log q(x) = log N(eps) - sum(log_sigma) -
+    sum(log x + log(1-x)) (density of expit(mu + sigma*eps) by the change-of-variables formula)."""
+    import oracle.prob as oprob
+
+    rng = np.random.default_rng(4)
+    for d in (1, 5, 40):
+        prm = {"mu": torch.tensor(rng.normal(0, 1, d)), "log_sigma": torch.tensor(rng.normal(-0.3, 0.5, d))}
+        eps = torch.tensor(rng.standard_normal(d))
+        x = oprob.z1_sample(prm, eps)
+        want = (-0.5 * eps**2 - 0.5 * np.log(2 * np.pi)).sum() - prm["log_sigma"].sum() - (torch.log(x) + torch.log(1 - x)).sum()
+        assert abs(oprob.z1_log_pdf(prm, x).item() - want.item()) <= 1e-12 * abs(want.item())
+        # round trip through the inverse map
+        z = oprob.zero_one_inverse(x)
+        np.testing.assert_allclose(oprob.diagonal_affine_inverse(prm, z).numpy(), eps.numpy(), rtol=1e-9, atol=1e-12)
