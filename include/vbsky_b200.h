@@ -78,6 +78,18 @@ int vbsky_encode_tips(const char* seqs, int64_t n, int64_t L, uint8_t* codes);
 int vbsky_compress_patterns(const uint8_t* codes, int64_t L, int64_t n, const int64_t* perm,
                             uint8_t* patterns, int64_t* counts, int64_t* S_out);
 
+/* Device versions (one CTA per alignment; same results bit for bit): seqs dev [n][L] chars ->
+ * codes dev [L][n]; codes dev [T][L][n] (+ optional perm dev [T][n]) -> patterns dev [T][L][n]
+ * (first S_out[t] rows valid), counts dev [T][L], S_out dev [T].  The radix sort is a stable
+ * counting sort per tip column on the bit-reversed masks, least significant column first.
+ * vbsky_encode_tips_device synchronises the stream (it reports the KeyError position).          */
+int vbsky_encode_tips_device(const char* seqs, int64_t n, int64_t L, uint8_t* codes,
+                             int64_t* bad_index, void* stream);
+size_t vbsky_compress_workspace_bytes(int32_t T, int64_t L);
+int vbsky_compress_patterns_device(int32_t T, int64_t L, int32_t n, const uint8_t* codes,
+                                   const int32_t* perm, uint8_t* patterns, int64_t* counts,
+                                   int32_t* S_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Tree layout: an ensemble of T trees with n tips each, given as the reference's TreeData
  * arrays (tree_data.py:17-23).  Builds, per tree, the evaluation schedules of the pruning

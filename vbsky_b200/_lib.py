@@ -61,6 +61,9 @@ SIGNATURES = {
     "vbsky_subst_rate_matrix": (C.c_int, [C.POINTER(SubstModel), _f64p]),
     "vbsky_encode_tips": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _u8p]),
     "vbsky_compress_patterns": (C.c_int, [_u8p, C.c_int64, C.c_int64, _i64p, _u8p, _i64p, _i64p]),
+    "vbsky_encode_tips_device": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _i64p, _vp]),
+    "vbsky_compress_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "vbsky_compress_patterns_device": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vbsky_layout_create": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, C.POINTER(_vp)]),
     "vbsky_layout_destroy": (None, [_vp]),
     "vbsky_layout_info": (C.c_int, [_vp, _i32p]),

@@ -60,3 +60,49 @@ def pad_tips(tips: List[PackedTips]) -> List[PackedTips]:
         counts = np.concatenate([t.counts, np.zeros(pad)])
         out.append(PackedTips(patterns, counts))
     return out
+
+
+def compress_patterns_device(codes, perm=None):
+    """Device version of ``compress_patterns`` for a batch of alignments: ``codes`` CUDA uint8 tensor
+    [T, L, n] of state masks (or [L, n]), optional ``perm`` CUDA int32 [T, n].  Returns a list of
+    (patterns uint8 [S_t, n], counts int64 [S_t]) CUDA tensors, bit-identical to the host path."""
+    import torch
+
+    single = codes.dim() == 2
+    if single:
+        codes = codes[None]
+        perm = None if perm is None else perm[None]
+    codes = codes.contiguous()
+    T, L, n = codes.shape
+    dev = codes.device
+    patterns = torch.empty_like(codes)
+    counts = torch.empty((T, L), dtype=torch.int64, device=dev)
+    S = torch.empty(T, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = _lib.lib.vbsky_compress_workspace_bytes(T, L)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        pp = C.c_void_p(0 if perm is None else perm.contiguous().data_ptr())
+        _lib.check(_lib.lib.vbsky_compress_patterns_device(
+            T, L, n, C.c_void_p(codes.data_ptr()), pp, C.c_void_p(patterns.data_ptr()), C.c_void_p(counts.data_ptr()),
+            C.c_void_p(S.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes, st))
+    Sh = S.cpu().tolist()
+    out = [(patterns[t, : Sh[t]], counts[t, : Sh[t]]) for t in range(T)]
+    return out[0] if single else out
+
+
+def encode_codes_device(seqs, device):
+    """Device version of ``encode_codes``: n equal-length sequences -> CUDA uint8 [L, n] masks."""
+    import torch
+
+    seqs = [s if isinstance(s, str) else "".join(s) for s in seqs]
+    n, L = len(seqs), len(seqs[0])
+    if any(len(s) != L for s in seqs):
+        raise ValueError("sequences must have equal length")
+    raw = torch.frombuffer(bytearray("".join(seqs).encode("latin-1")), dtype=torch.uint8).to(device)
+    codes = torch.empty((L, n), dtype=torch.uint8, device=device)
+    bad = C.c_int64(-1)
+    with torch.cuda.device(device):
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(_lib.lib.vbsky_encode_tips_device(C.c_void_p(raw.data_ptr()), n, L, C.c_void_p(codes.data_ptr()), C.byref(bad), st))
+    return codes
