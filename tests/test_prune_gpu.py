@@ -134,3 +134,54 @@ def test_prune_zero_length_branches_use_literal_clips(cuda):
         if ok.all():
             np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
     ens.close()
+
+
+@pytest.mark.parametrize("n,S,caterpillar", [(1500, 384, False), (900, 200, True), (4096, 130, False)])
+def test_prune_large_trees_vs_c_port(cuda, n, S, caterpillar):
+    """Large / degenerate topologies (config-5 sweep sizes) against the C/OpenMP oracle port, which is fast
+    enough there; the NumPy oracle cross-checks the C port in tests/test_oracle_selfcheck.py."""
+    import oracle.cref as cref
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY
+    from vbsky_b200.synth import evolve_codes, random_tree, sample_heights
+    from vbsky_b200.tips import PackedTips
+
+    rng = np.random.default_rng(n)
+    td = random_tree(n, rng, caterpillar=caterpillar)
+    Q, oQ = HKY(2.7), osub.HKY(2.7)
+    sh = sample_heights(td, 1, rng, origin=1.0)
+    bl = sh.branch_lengths * (0.02 if not caterpillar else 0.002)
+    codes = evolve_codes(td, bl[0], oQ, S, rng, missing=0.02)
+    counts = rng.integers(1, 3, S).astype(np.float64)
+    ens = Ensemble([td], [PackedTips(codes, counts)], Q, device=cuda)
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), torch.zeros(1, dtype=torch.int32, device=cuda),
+                              want_grad=True, want_site_ll=True)
+    tot, g, sll = cref.prune(_oracle_td(td), bl[0], oQ, codes, counts, True, True)
+    np.testing.assert_allclose(site[0].cpu().numpy(), sll, rtol=LL_RTOL, atol=1e-11)
+    np.testing.assert_allclose(ll[0].item(), tot, rtol=LL_RTOL)
+    np.testing.assert_allclose(dll[0].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    ens.close()
+
+
+def test_prune_many_units_single_pattern(cuda):
+    """Ragged extremes: one site pattern (S=1, a single partly-filled tile) and thousands of units."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, codes_to_partials
+    from vbsky_b200.synth import random_tree, sample_heights
+    from vbsky_b200.tips import PackedTips
+
+    rng = np.random.default_rng(11)
+    n, U = 9, 3000
+    td = random_tree(n, rng)
+    Q, oQ = HKY(2.7), osub.HKY(2.7)
+    codes = rng.choice(np.array([1, 2, 4, 8, 15], dtype=np.uint8), (1, n))
+    ens = Ensemble([td], [PackedTips(codes, np.array([3.0]))], Q, device=cuda)
+    bl = sample_heights(td, U, rng, origin=1.0).branch_lengths * 0.3
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), torch.zeros(U, dtype=torch.int32, device=cuda),
+                              want_grad=True, want_site_ll=True)
+    for u in (0, 1, U // 2, U - 1):
+        tot, g, sll = oprune.data_loglik_and_grad(bl[u], oQ, codes_to_partials(codes), np.array([3.0]), _oracle_td(td))
+        np.testing.assert_allclose(ll[u].item(), tot, rtol=LL_RTOL)
+        np.testing.assert_allclose(site[u].cpu().numpy(), sll, rtol=LL_RTOL, atol=LL_ATOL)
+        np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    ens.close()
