@@ -1,0 +1,98 @@
+"""Batched ELBO over an ensemble and a minimal optimiser loop on top of the CUDA path.
+
+Host-side mirror of ``optim.loss`` (optim.py:35-78) and of the Adagrad loop of ``SeqData.loop``
+(fasta.py:387-487) for the *batched* objective the multi-GPU design evaluates: all trees at the same
+global parameters, K Monte-Carlo samples each (the reference visits trees one at a time).
+
+    ELBO = mean_k [ sum_t loglik(theta_k, local_{t,k}) + log prior(theta_k) ]
+           - mean_k log q_global(theta_k) - sum_t mean_k log q_t(local_{t,k})
+
+Global flows are the reference's defaults (fasta.py:366-375): origin ~ pos(1), R ~ pos(m) with
+pos = Compose(DiagonalAffine, Exp); delta, s, rho_m, clock_rate constants.  Those few elementwise maps stay in
+PyTorch (the reference keeps them in JAX); the local flows, heights, tree prior and pruning run in the kernels.
+"""
+import math
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import bdsky
+from .ensemble import Ensemble
+from .flows import local_flow
+
+
+def _pos_sample(p: Dict[str, torch.Tensor], eps: torch.Tensor):
+    """Transform(dim, Compose(DiagonalAffine, Exp)) over MeanField (transform.py:130-166): x = exp(mu + sigma*eps),
+    log q(x) = log N(eps) - sum(log_sigma) - sum(mu + sigma*eps)."""
+    z = p["mu"] + torch.exp(p["log_sigma"]) * eps
+    logq = (-0.5 * eps**2 - 0.5 * math.log(2 * math.pi)).sum(-1) - p["log_sigma"].sum() - z.sum(-1)
+    return torch.exp(z), logq
+
+
+class EnsembleELBO:
+    def __init__(self, ens: Ensemble, K: int, m: int, delta: float = 36.5, s: float = 0.02, clock_rate: float = 1.12e-3,
+                 prior_fn: Optional[Callable[[Dict[str, torch.Tensor]], torch.Tensor]] = None, seed: int = 0):
+        self.ens, self.K, self.m = ens, K, m
+        dev = ens.device
+        T, n = ens.T, ens.n
+        self.unit_tree = torch.arange(T, dtype=torch.int32, device=dev).repeat_interleave(K)
+        self.origin_start = torch.tensor([float(td.sample_times.max()) for td in ens.tds], dtype=torch.float64, device=dev)
+        self.const = dict(delta=delta, s=s, clock_rate=clock_rate)
+        self.prior_fn = prior_fn
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed)
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float64, device=dev)
+        # variational parameters (the reference initialises them with N(0, 0.1); fasta.py:439-446)
+        self.params = {
+            "origin": {"mu": z(1), "log_sigma": z(1)},
+            "R": {"mu": z(m), "log_sigma": z(m)},
+            "local": {"mu": z(T, n - 1), "log_sigma": z(T, n - 1)},  # [proportions (n-2), root_proportion]
+        }
+        for grp in self.params.values():
+            for k, v in grp.items():
+                v.copy_(0.1 * torch.randn(v.shape, dtype=torch.float64, device=dev, generator=self.gen))
+                v.requires_grad_(True)
+
+    def leaves(self):
+        return [v for grp in self.params.values() for v in grp.values()]
+
+    def elbo(self) -> torch.Tensor:
+        ens, K, m = self.ens, self.K, self.m
+        T, n, dev = ens.T, ens.n, ens.device
+        U = T * K
+        rnd = lambda *shape: torch.randn(*shape, dtype=torch.float64, device=dev, generator=self.gen)
+        origin, lq_o = _pos_sample(self.params["origin"], rnd(K, 1))
+        R, lq_r = _pos_sample(self.params["R"], rnd(K, m))
+        x, lq_local = local_flow(self.params["local"]["mu"], self.params["local"]["log_sigma"], rnd(U, n - 1), self.unit_tree)
+        ks = torch.arange(K, device=dev).repeat(T)  # sample index of each unit
+        full = lambda v: torch.full((U, m), v, dtype=torch.float64, device=dev)
+        p = {
+            "proportions": x[:, : n - 2], "root_proportion": x[:, n - 2],
+            "origin": origin[ks, 0], "origin_start": self.origin_start[self.unit_tree.long()],
+            "clock_rate": torch.full((U,), self.const["clock_rate"], dtype=torch.float64, device=dev),
+            "R": R[ks], "delta": full(self.const["delta"]), "s": full(self.const["s"]),
+            "rho": torch.zeros(U, m, dtype=torch.float64, device=dev),
+        }
+        ll = bdsky.loglik(p, ens, self.unit_tree, c=(False, True, True))
+        val = ll.sum() / K - lq_o.mean() - lq_r.mean() - lq_local.sum() / K
+        if self.prior_fn is not None:
+            val = val + self.prior_fn({"origin": origin, "R": R}).mean()
+        return val
+
+    def fit(self, n_iter: int = 10, step_size: float = 1.0, callback=None):
+        """Adagrad on -ELBO (jax.example_libraries.optimizers.adagrad of fasta.py:388: x -= lr * g / sqrt(sum g^2),
+        momentum 0.9 on the squared-gradient accumulator is the library default there; torch's Adagrad is the
+        plain accumulator)."""
+        opt = torch.optim.Adagrad(self.leaves(), lr=step_size)
+        hist = []
+        for i in range(n_iter):
+            opt.zero_grad(set_to_none=True)
+            loss = -self.elbo()
+            loss.backward()
+            for v in self.leaves():
+                v.grad.nan_to_num_()  # fasta.py:421,427
+            opt.step()
+            hist.append(loss.item())
+            if callback:
+                callback(i, loss.item())
+        return hist
