@@ -148,6 +148,16 @@ int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, 
                                const vbsky_subst_model* model, double* site_ll, double* ll,
                                double* dll_dbl, void* ws, size_t ws_bytes, void* stream);
 
+/* Same call with fp32 messages / tables / scratch (half the HBM traffic, FP32 pipe); inputs and
+ * outputs stay fp64, P(t) is built in fp64 and rounded once, the final log and all sums over
+ * patterns are fp64.  Accuracy target of BASELINE.json: 1e-5 relative on log-likelihoods.      */
+size_t vbsky_prune_workspace_bytes_f32(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                       int32_t want_grad);
+int vbsky_prune_value_and_grad_f32(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                   const int32_t* unit_tree, const double* bl,
+                                   const vbsky_subst_model* model, double* site_ll, double* ll,
+                                   double* dll_dbl, void* ws, size_t ws_bytes, void* stream);
+
 /* Counters of the last prune call made by this thread: out[0]=kernel launches,
  * out[1]=persistent CTAs, out[2]=sites per CTA tile, out[3]=dynamic smem bytes per CTA,
  * out[4]=algorithmic HBM bytes of the fused pruning kernel (DESIGN.md formula).               */
@@ -217,11 +227,13 @@ int vbsky_bdsky_value_and_grad(int32_t U, int32_t n, int32_t m, const double* la
 /* bdsky.loglik (bdsky.py:268-345) without the user prior term c[0]: for every unit
  *   ll = [flags&1] _tree_loglik(...) + [flags&2] sum_s counts[s] * prune_loglik(...)
  * and the gradient w.r.t. every field of vbsky_params (grads == NULL => value only).
- * flags: bit0 tree-prior term (c[1]), bit1 data term (c[2]), bit2 condition_on_survival.
+ * flags: bit0 tree-prior term (c[1]), bit1 data term (c[2]), bit2 condition_on_survival,
+ * bit3 fp32 pruning kernels.
  * ll_tree / ll_data [U] may be NULL.  Six kernel launches, no host synchronisation.            */
 #define VBSKY_TERM_TREE 1
 #define VBSKY_TERM_DATA 2
 #define VBSKY_CONDITION_ON_SURVIVAL 4
+#define VBSKY_PRUNE_F32 8 /* evaluate the data term with the fp32 pruning kernels */
 size_t vbsky_loglik_workspace_bytes(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, int32_t m);
 int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
                                 const int32_t* unit_tree, int32_t m, const vbsky_params* in,

@@ -185,3 +185,26 @@ def test_prune_many_units_single_pattern(cuda):
         np.testing.assert_allclose(site[u].cpu().numpy(), sll, rtol=LL_RTOL, atol=LL_ATOL)
         np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
     ens.close()
+
+
+@pytest.mark.parametrize("T,n,S,K,clock", [(2, 10, 300, 2, 0.05), (1, 200, 1000, 2, 1.12e-3), (1, 500, 600, 1, 1.0)])
+def test_prune_fp32_mode(cuda, T, n, S, K, clock):
+    """fp32-storage kernels against the fp64 oracle: BASELINE.json's fp32 tolerance is 1e-5 relative on per-site and
+    total log-likelihoods (no gradient tolerance is stated for fp32; 1e-3 relative to the largest entry is checked)."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, codes_to_partials
+    from vbsky_b200.synth import make_ensemble
+
+    data = make_ensemble(T, n, S, K, seed=n + S, Q=HKY(2.7), clock_rate=clock, missing=0.05)
+    ens = Ensemble(data.tds, data.tips, HKY(2.7), device=cuda)
+    bl = np.stack([data.heights[t].branch_lengths[k] for t in range(T) for k in range(K)]) * clock
+    ut = torch.as_tensor(np.repeat(np.arange(T, dtype=np.int32), K), device=cuda)
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), ut, want_grad=True, want_site_ll=True, precision="f32")
+    for u in range(T * K):
+        t = u // K
+        tot, g, sll = oprune.data_loglik_and_grad(bl[u], osub.HKY(2.7), codes_to_partials(data.tips[t].patterns),
+                                                  data.tips[t].counts, _oracle_td(data.tds[t]))
+        np.testing.assert_allclose(site[u].cpu().numpy(), sll, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ll[u].item(), tot, rtol=1e-5)
+        np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=1e-3, atol=1e-3 * np.abs(g).max())
+    ens.close()

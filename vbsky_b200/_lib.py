@@ -75,6 +75,11 @@ SIGNATURES = {
         C.c_int,
         [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _vp, _vp, _vp, _vp, C.c_size_t, _vp],
     ),
+    "vbsky_prune_workspace_bytes_f32": (C.c_size_t, [_vp, _vp, C.c_int32, C.c_int32]),
+    "vbsky_prune_value_and_grad_f32": (
+        C.c_int,
+        [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _vp, _vp, _vp, _vp, C.c_size_t, _vp],
+    ),
     "vbsky_prune_last_stats": (C.c_int, [_i64p]),
     "vbsky_prune_timing": (C.c_int, [C.c_int32, _f64p, _i64p]),
     "vbsky_local_flow_sample": (C.c_int, [C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

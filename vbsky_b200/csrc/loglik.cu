@@ -36,7 +36,7 @@ static int loglik_plan(const vbsky_layout* lay, const vbsky_tips* tips, int U, i
   pl->lt = take(U * d), pl->ld = take(U * d), pl->dh = take(U * N * d);
   pl->bdsky_bytes = vbsky_bdsky_workspace_bytes(U, lay->n);
   pl->bdsky = take(pl->bdsky_bytes);
-  pl->prune_bytes = vbsky_prune_workspace_bytes(lay, tips, U, 1);
+  pl->prune_bytes = std::max(vbsky_prune_workspace_bytes(lay, tips, U, 1), vbsky_prune_workspace_bytes_f32(lay, tips, U, 1));
   if (pl->prune_bytes == 0) return VBSKY_EINVAL;
   pl->prune = take(pl->prune_bytes);
   pl->total = off;
@@ -94,8 +94,11 @@ extern "C" int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_
     VB_CUDA(cudaMemsetAsync(grads->rho, 0, (size_t)U * m * sizeof(double), st));
   }
   if (data) {
-    rc = vbsky_prune_value_and_grad(lay, tips, U, unit_tree, D(pl.bl), model, nullptr, D(pl.ld), grads ? D(pl.dbl) : nullptr,
-                                    b + pl.prune, pl.prune_bytes, stream);
+    rc = (flags & VBSKY_PRUNE_F32)
+             ? vbsky_prune_value_and_grad_f32(lay, tips, U, unit_tree, D(pl.bl), model, nullptr, D(pl.ld),
+                                              grads ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream)
+             : vbsky_prune_value_and_grad(lay, tips, U, unit_tree, D(pl.bl), model, nullptr, D(pl.ld),
+                                          grads ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream);
     if (rc != VBSKY_OK) return rc;
   }
   combine_kernel<<<(U + 127) / 128, 128, 0, st>>>(U, flags, D(pl.lt), D(pl.ld), ll, ll_tree, ll_data);

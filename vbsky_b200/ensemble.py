@@ -98,9 +98,15 @@ class Ensemble:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def prune(self, bl: torch.Tensor, unit_tree: torch.Tensor, want_grad: bool = True, want_site_ll: bool = False):
+    def prune(self, bl: torch.Tensor, unit_tree: torch.Tensor, want_grad: bool = True, want_site_ll: bool = False,
+              precision: str = "f64"):
         """bl [U, 2n-2] fp64 (already multiplied by the clock rate), unit_tree [U] int32, both on the
-        device.  Returns (ll [U], dll_dbl [U, 2n-2] or None, site_ll [U, S] or None)."""
+        device.  Returns (ll [U], dll_dbl [U, 2n-2] or None, site_ll [U, S] or None).
+        ``precision="f32"`` runs the fp32-storage kernels (inputs/outputs stay fp64; 1e-5 tolerance)."""
+        if precision not in ("f64", "f32"):
+            raise ValueError("precision must be 'f64' or 'f32'")
+        f_ws = _lib.lib.vbsky_prune_workspace_bytes if precision == "f64" else _lib.lib.vbsky_prune_workspace_bytes_f32
+        f_run = _lib.lib.vbsky_prune_value_and_grad if precision == "f64" else _lib.lib.vbsky_prune_value_and_grad_f32
         U = bl.shape[0]
         if bl.dtype != torch.float64 or bl.device != self.device or bl.shape != (U, 2 * self.n - 2):
             raise ValueError(f"bl must be a float64 [{U}, {2 * self.n - 2}] tensor on {self.device}")
@@ -108,7 +114,7 @@ class Ensemble:
             raise ValueError("unit_tree must be an int32 [U] tensor on the ensemble's device")
         bl = bl.contiguous()
         with torch.cuda.device(self.device):
-            need = _lib.lib.vbsky_prune_workspace_bytes(self._layout, self._tips, U, int(want_grad))
+            need = f_ws(self._layout, self._tips, U, int(want_grad))
             if need == 0:
                 raise _lib.VbskyError(-1, _lib.last_error())
             ws = self._workspace(need)
@@ -116,7 +122,7 @@ class Ensemble:
             dll = torch.empty(U, 2 * self.n - 2, dtype=torch.float64, device=self.device) if want_grad else None
             site = torch.empty(U, self.S, dtype=torch.float64, device=self.device) if want_site_ll else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(_lib.lib.vbsky_prune_value_and_grad(
+            _lib.check(f_run(
                 self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model),
                 _ptr(site), _ptr(ll), _ptr(dll), _ptr(ws), ws.numel(), C.c_void_p(stream)))
         return ll, dll, site
