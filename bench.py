@@ -33,7 +33,7 @@ WORKLOADS = {
 }
 KAPPA = 2.7
 M_INTERVALS = 50  # skyline intervals (paper/covid.py m=50)
-NCU_DRAM_BYTES_CONFIG3 = 203.299431e9 + 191.150824e9
+NCU_DRAM_BYTES_CONFIG3 = 203.267860e9 + 191.123422e9
 UNIT = "ELBO+grad evals/s"
 METRIC = "elbo_grad_evals_per_sec"
 
@@ -244,7 +244,7 @@ def main():
     stats = ens.last_stats()
     ll_dev = out["ll"].cpu().numpy()
 
-    # ---- end-to-end through the host-buffer C ABI: pinned params -> H2D -> 7 kernels -> D2H of ll + every gradient
+    # ---- end-to-end through the host-buffer C ABI: pinned params -> H2D -> 8 kernels -> D2H of ll + every gradient
     pin = lambda a: torch.as_tensor(a).pin_memory().numpy()
     hp = {k: pin(v) for k, v in host.items()}
     hut = pin(ut_host)
@@ -300,7 +300,7 @@ def main():
         },
         "e2e": {"value": 1e3 / e2e_ms.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "vbsky_loglik_value_and_grad_host: pinned host parameters in, ll + all gradients out, per step; tip codes resident (uploaded once, as prep_data is one-off in the reference)"},
-        "gpu_launches": int(7 * args.steps),
+        "gpu_launches": int(8 * args.steps),  # chain_forward, bdsky, tables, prune x2 (clip-free + literal-clip units), finalize, combine, chain_backward
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "kernel": "prune_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -229,7 +229,7 @@ int vbsky_bdsky_value_and_grad(int32_t U, int32_t n, int32_t m, const double* la
  * and the gradient w.r.t. every field of vbsky_params (grads == NULL => value only).
  * flags: bit0 tree-prior term (c[1]), bit1 data term (c[2]), bit2 condition_on_survival,
  * bit3 fp32 pruning kernels.
- * ll_tree / ll_data [U] may be NULL.  Six kernel launches, no host synchronisation.            */
+ * ll_tree / ll_data [U] may be NULL.  Eight kernel launches, no host synchronisation.            */
 #define VBSKY_TERM_TREE 1
 #define VBSKY_TERM_DATA 2
 #define VBSKY_CONDITION_ON_SURVIVAL 4
