@@ -29,6 +29,7 @@ WORKLOADS = {
     "config3": (100, 200, 29903, 10, 1.12e-3),
     "config2": (1, 500, 10000, 16, 1.0),
     "config4": (1000, 50, 2000, 10, 1.12e-3),
+    "config1": (10, 10, 134, 10, 1.12e-3),  # HCV-example shape (example.ipynb: 10 trees x 10 tips, ~134 patterns)
     "tiny": (4, 16, 300, 2, 1.12e-3),
 }
 KAPPA = 2.7
