@@ -128,6 +128,9 @@ typedef struct vbsky_tips vbsky_tips;
 int vbsky_tips_create(const vbsky_layout* lay, int64_t S, const uint8_t* patterns,
                       const double* counts, vbsky_tips** out);
 void vbsky_tips_destroy(vbsky_tips* tips);
+/* Replace the pattern weights (host [T][S]) of an existing tips object; synchronous.  Used to obtain
+ * d/d bl of sum_s w[s] * site_ll[s] for arbitrary cotangents w (the vmapped prune_loglik's transpose). */
+int vbsky_tips_set_counts(vbsky_tips* tips, const double* counts);
 
 /* ------------------------------------------------------------------------------------------
  * Pruning likelihood and gradient.  Replaces, for all units at once,

@@ -208,3 +208,28 @@ def test_prune_fp32_mode(cuda, T, n, S, K, clock):
         np.testing.assert_allclose(ll[u].item(), tot, rtol=1e-5)
         np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=1e-3, atol=1e-3 * np.abs(g).max())
     ens.close()
+
+
+def test_prune_loglik_reference_signature(cuda):
+    """prune.prune_loglik(branch_lengths, Q, tip_partials, td) with the reference's signature (prune.py:99-131),
+    vmapped over patterns by passing [S, n, 4]; its gradient is eq. (9) pulled back through the kernel."""
+    from vbsky_b200.prune import prune_loglik
+    from vbsky_b200.substitution import HKY, codes_to_partials
+    from vbsky_b200.synth import evolve_codes, random_tree, sample_heights
+
+    rng = np.random.default_rng(21)
+    n, S = 11, 70
+    td = random_tree(n, rng)
+    Q, oQ = HKY(2.7), osub.HKY(2.7)
+    bl = sample_heights(td, 1, rng, origin=1.0).branch_lengths[0] * 0.2
+    part = codes_to_partials(evolve_codes(td, bl, oQ, S, rng, missing=0.05))
+    w = rng.normal(size=S)
+    tbl = torch.tensor(bl, device=cuda, requires_grad=True)
+    ll = prune_loglik(tbl, Q, part, td)
+    (ll * torch.tensor(w, device=cuda)).sum().backward()
+    want_ll, want_g = oprune.prune_loglik_and_grad(bl, oQ, part, _oracle_td(td))
+    np.testing.assert_allclose(ll.detach().cpu().numpy(), want_ll, rtol=LL_RTOL, atol=LL_ATOL)
+    g = (want_g * w[:, None]).sum(0)
+    np.testing.assert_allclose(tbl.grad.cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    single = prune_loglik(torch.tensor(bl, device=cuda), Q, part[0], td)  # [n, 4] -> scalar, as in the reference
+    assert single.dim() == 0 and abs(single.item() - want_ll[0]) <= LL_RTOL * abs(want_ll[0]) + LL_ATOL

@@ -70,6 +70,7 @@ SIGNATURES = {
     "vbsky_layout_get": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _f64p, _i32p]),
     "vbsky_tips_create": (C.c_int, [_vp, C.c_int64, _u8p, _f64p, C.POINTER(_vp)]),
     "vbsky_tips_destroy": (None, [_vp]),
+    "vbsky_tips_set_counts": (C.c_int, [_vp, _f64p]),
     "vbsky_prune_workspace_bytes": (C.c_size_t, [_vp, _vp, C.c_int32, C.c_int32]),
     "vbsky_prune_value_and_grad": (
         C.c_int,

@@ -212,3 +212,10 @@ extern "C" int vbsky_tips_create(const vbsky_layout* lay, int64_t S, const uint8
   *out = tp;
   return VBSKY_OK;
 }
+
+extern "C" int vbsky_tips_set_counts(vbsky_tips* tips, const double* counts) {
+  VB_CHECK_ARG(tips && counts, "NULL argument");
+  VB_CUDA(cudaMemcpy2D(tips->d_counts, tips->S_pad * sizeof(double), counts, tips->S * sizeof(double), tips->S * sizeof(double),
+                       tips->T, cudaMemcpyHostToDevice));
+  return VBSKY_OK;
+}

@@ -92,6 +92,12 @@ class Ensemble:
                                               _lib.np_ptr(sib, C.c_int32)))
         return dict(up=up, down=down, down_nodes=dn, lower_sampling_times=lst, siblings=sib)
 
+    def set_counts(self, counts: np.ndarray):
+        """Replace the pattern weights [T, S] on the device (synchronous)."""
+        counts = np.ascontiguousarray(counts, dtype=np.float64).reshape(self.T, self.S)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.vbsky_tips_set_counts(self._tips, _lib.np_ptr(counts, C.c_double)))
+
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None

@@ -13,26 +13,24 @@ from .tree_data import TreeData
 
 
 class _PruneSites(torch.autograd.Function):
+    """Per-pattern log-likelihoods of one tree; the cotangent g [S] is pulled back with one more kernel call in
+    which the pattern weights are g (d/d bl of sum_s g[s] * ll_s is exactly what the kernel accumulates)."""
+
     @staticmethod
     def forward(ctx, bl, ens):
-        # one unit per site-weight vector would be wasteful; per-site gradients are obtained by a
-        # unit-count pattern trick only when needed.  Here: value per site + total gradient pieces.
         unit_tree = torch.zeros(1, dtype=torch.int32, device=bl.device)
-        ll, dll, site = ens.prune(bl[None].contiguous(), unit_tree, want_grad=False, want_site_ll=True)
+        _, _, site = ens.prune(bl[None].contiguous(), unit_tree, want_grad=False, want_site_ll=True)
         ctx.ens = ens
         ctx.save_for_backward(bl)
         return site[0]
 
     @staticmethod
     def backward(ctx, gout):
-        # d/dbl sum_s gout[s] * ll_s: re-run the kernel with counts = gout
         (bl,) = ctx.saved_tensors
         ens = ctx.ens
-        w = gout.detach().double().cpu().numpy()
-        ens2 = Ensemble(ens.tds, [PackedTips(ens._patterns, w)], ens.Q, device=bl.device)
+        ens.set_counts(gout.detach().double().cpu().numpy()[None])
         unit_tree = torch.zeros(1, dtype=torch.int32, device=bl.device)
-        _, dll, _ = ens2.prune(bl[None].contiguous(), unit_tree, want_grad=True)
-        ens2.close()
+        _, dll, _ = ens.prune(bl[None].contiguous(), unit_tree, want_grad=True)
         return dll[0], None
 
 
@@ -55,6 +53,5 @@ def prune_loglik(branch_lengths, Q: SubstitutionModel, tip_partials, td: TreeDat
     assert bl.ndim == 1 and bl.shape[0] == 2 * (td.n - 1)
     patterns = partials_to_codes(tp)
     ens = Ensemble([td], [PackedTips(patterns, np.ones(len(patterns)))], Q, device=bl.device)
-    ens._patterns = patterns
     out = _PruneSites.apply(bl, ens)
     return out[0] if single else out
