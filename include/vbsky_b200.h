@@ -91,6 +91,32 @@ int vbsky_compress_patterns_device(int32_t T, int64_t L, int32_t n, const uint8_
                                    int32_t* S_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Starting trees (SeqData.sample_trees, fasta.py:203-296), batched over the T subsamples.
+ *
+ * vbsky_snp_pack_device: seqs dev [N][L] chars -> planes dev [N][4][ceil(L/32)] bit planes
+ * (A, C, G, T after upper-casing; everything else is "ignored"), once per alignment.
+ * vbsky_snp_dists_device: what `snp-dists -b` prints for the subsample rows[t][0..n) of the
+ * alignment (fasta.py:268-281): dist dev [T][n][n] int32, dist[r][c] = #columns where the two
+ * characters differ and both are in AGTC.
+ * vbsky_supgma_distances_device: get_distance_matrix (upgma.py:25-62) on dist's lower triangle
+ * and times dev [T][n]: omega[t] = last coefficient of the least-squares fit (one intercept
+ * per time class of the later sample, or a single intercept when single_theta), and
+ * D dev [T][n][n] (symmetric, zero diagonal) = y + omega (t_r + t_c - 2 min t).
+ * vbsky_upgma_device: Bio.Phylo's DistanceTreeConstructor.upgma (fasta.py:283) on D (which is
+ * overwritten): merges dev [T][n-1][2] = (clade1, clade2) of the k-th inner clade in child
+ * order, a clade being a tip position < n or n + (index of an earlier merge); heights dev
+ * [T][n-1] = min_dist / 2.  Ties are broken as Biopython's scan does (last `>=` hit); the new
+ * row is the plain average of the two merged rows.  n <= 1024.                                */
+size_t vbsky_snp_planes_bytes(int64_t N, int64_t L);
+int vbsky_snp_pack_device(const char* seqs, int64_t N, int64_t L, uint32_t* planes, void* stream);
+int vbsky_snp_dists_device(const uint32_t* planes, int64_t N, int64_t L, const int32_t* rows,
+                           int32_t T, int32_t n, int32_t* dist, void* stream);
+int vbsky_supgma_distances_device(int32_t T, int32_t n, const int32_t* dist, const double* times,
+                                  int32_t single_theta, double* D, double* omega, void* stream);
+int vbsky_upgma_device(int32_t T, int32_t n, double* D, int32_t* merges, double* heights,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Tree layout: an ensemble of T trees with n tips each, given as the reference's TreeData
  * arrays (tree_data.py:17-23).  Builds, per tree, the evaluation schedules of the pruning
  * kernel (a depth-first order that keeps all live partial vectors on chip), the level order

@@ -24,3 +24,35 @@ def test_fit_improves_elbo(cuda):
     for v in model.leaves():
         assert v.grad is not None and torch.isfinite(v.grad).all()
     ens.close()
+
+
+def test_alignment_to_fit_pipeline(cuda):
+    """prep_data end to end on the device (fasta.py:333-360): subsample -> starting trees -> tip patterns ->
+    ensemble handles -> a few Adagrad steps of the batched ELBO."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.fit import EnsembleELBO
+    from vbsky_b200.substitution import HKY
+    from vbsky_b200.synth import evolve_codes, random_tree, sample_heights
+    from vbsky_b200.tips import pad_tips, process_tips
+    from vbsky_b200.treebuild import PackedAlignment, sample_trees
+
+    rng = np.random.default_rng(2)
+    N, L, T, n = 30, 600, 3, 10
+    td = random_tree(N, rng)
+    bl = sample_heights(td, 1, rng, origin=1.0).branch_lengths[0] * 0.05
+    codes = evolve_codes(td, bl, HKY(2.7), L, rng)  # [L, N] masks
+    letters = np.full(16, "N")
+    letters[[1, 2, 4, 8]] = list("ACGT")
+    seqs = ["".join(letters[codes[:, i]]) for i in range(N)]
+    names = [f"s{i}" for i in range(N)]
+    sample_times = {names[i]: float(td.sample_times[i]) for i in range(N)}
+    rows = np.stack([rng.choice(N, n, replace=False) for _ in range(T)])
+    aln = PackedAlignment(seqs, cuda)
+    tds, maps, omega = sample_trees(aln, names, sample_times, rows)
+    assert np.isfinite(omega).all()
+    tips = pad_tips([process_tips([names[i] for i in rows[t]], [seqs[i] for i in rows[t]], maps[t]) for t in range(T)])
+    ens = Ensemble(tds, tips, HKY(2.7), device=cuda)
+    model = EnsembleELBO(ens, K=4, m=5, delta=2.0, s=0.2, clock_rate=0.05, seed=3)
+    hist = model.fit(n_iter=5, step_size=0.1)
+    assert np.isfinite(hist).all()
+    ens.close()

@@ -64,6 +64,11 @@ SIGNATURES = {
     "vbsky_encode_tips_device": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _i64p, _vp]),
     "vbsky_compress_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "vbsky_compress_patterns_device": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vbsky_snp_planes_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "vbsky_snp_pack_device": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "vbsky_snp_dists_device": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int32, C.c_int32, _vp, _vp]),
+    "vbsky_supgma_distances_device": (C.c_int, [C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp, _vp]),
+    "vbsky_upgma_device": (C.c_int, [C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "vbsky_layout_create": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, C.POINTER(_vp)]),
     "vbsky_layout_destroy": (None, [_vp]),
     "vbsky_layout_info": (C.c_int, [_vp, _i32p]),
