@@ -235,3 +235,39 @@ def test_layout_rejects_malformed_trees():
         _layout([TreeData(td.postorder, td.child_parent, bad_pc, td.sample_times)])
     with pytest.raises(_lib.VbskyError):
         _layout([TreeData(td.postorder[::-1].copy(), td.child_parent, td.parent_child, td.sample_times)])
+
+
+def test_lognorm_logpdf_and_transform_match_scipy():
+    import torch
+    from scipy.stats import norm
+
+    from vbsky_b200.bdsky import bdsky_transform, lognorm_logpdf
+
+    x = np.array([-1.3, 0.0, 0.4, 2.2])
+    got = lognorm_logpdf(torch.as_tensor(x), 0.3, 0.5).numpy()
+    want = norm.logpdf((x - 0.3) / 0.5) - x - np.log(0.5)  # bdsky.py:230-231
+    assert np.allclose(got, want, rtol=1e-14, atol=1e-14)
+    p = {k: torch.as_tensor(v) for k, v in dict(R=[1.5, 2.0], delta=[3.0, 4.0], s=[0.1, 0.2], rho=[0.0, 0.3]).items()}
+    lam, psi, mu, rho = bdsky_transform(p)
+    assert np.allclose(lam, [4.5, 8.0]) and np.allclose(psi, [0.3, 0.8]) and np.allclose(mu, [2.7, 3.2]) and np.allclose(rho, [0.0, 0.3])
+
+
+def test_merges_to_tree_numbering_matches_newick_route():
+    """UPGMA merge list -> TreeData must number nodes exactly as the reference's write-Newick / from_newick round trip."""
+    import oracle.treebuild as otb
+    from vbsky_b200.treebuild import merges_to_newick, merges_to_tree
+
+    rng = np.random.default_rng(4)
+    n = 15
+    x = rng.random((n, 2))
+    D = np.linalg.norm(x[:, None] - x[None], axis=-1)
+    merges, heights, nested = otb.upgma(D, [f"t{i}" for i in range(n)])
+    names = [f"t{i}" for i in range(n)]
+    td, nm = merges_to_tree(merges, names, {s: float(i) for i, s in enumerate(names)})
+    want, want_map = otd.TreeData.from_newick(otb.nested_to_newick(nested))
+    assert np.array_equal(td.child_parent, want.child_parent) and np.array_equal(td.parent_child, want.parent_child)
+    assert np.array_equal(td.postorder, want.postorder)
+    assert all(nm[s] == want_map[s] for s in names)
+    assert all(td.sample_times[nm[s]] == float(i) for i, s in enumerate(names))
+    td2, map2 = TreeData.from_newick(merges_to_newick(merges, heights, names))
+    assert np.array_equal(td2.child_parent, td.child_parent) and all(map2[s] == nm[s] for s in names)

@@ -152,3 +152,12 @@ def bdsky_transform(params):
     lam = params["R"] * params["delta"]
     psi = params["s"] * params["delta"]
     return lam, psi, params["delta"] - psi, params["rho"]
+
+
+def lognorm_logpdf(log_x, mu, sigma):
+    """Log-normal log-density in terms of log x (bdsky.py:230-231); used by callers' parameter priors."""
+    import math
+
+    sigma = torch.as_tensor(sigma, dtype=log_x.dtype, device=log_x.device)
+    z = (log_x - mu) / sigma
+    return -0.5 * z * z - 0.5 * math.log(2.0 * math.pi) - log_x - torch.log(sigma)

@@ -461,7 +461,7 @@ extern "C" int vbsky_bdsky_value_and_grad(int32_t U, int32_t n, int32_t m, const
 static int fill_chain(const vbsky_layout* lay, int32_t U, const int32_t* unit_tree, int32_t m, const vbsky_params* in,
                       ChainParams* p) {
   VB_CHECK_ARG(lay && unit_tree && in, "NULL argument");
-  VB_CHECK_ARG(lay->device >= 0, "layout was created without a CUDA device; there is no CPU fallback");
+  VB_CHECK_DEVICE(lay);
   VB_CHECK_ARG(U >= 1 && m >= 0, "bad shape U=%d m=%d", U, m);
   VB_CHECK_ARG((in->proportions || lay->n == 2) && in->root_proportion && in->origin && in->origin_start && in->clock_rate, "NULL parameter array");
   *p = ChainParams{};

@@ -28,6 +28,15 @@ int set_error(int code, const char* fmt, ...);
                                 cudaGetErrorString(_e), __FILE__, __LINE__);            \
   } while (0)
 
+// Handles live on the device that was current when they were created; every compute entry point requires it current.
+#define VB_CHECK_DEVICE(lay)                                                                         \
+  do {                                                                                               \
+    VB_CHECK_ARG((lay)->device >= 0, "layout was created without a CUDA device; there is no CPU fallback"); \
+    int _cur = -1;                                                                                   \
+    VB_CUDA(cudaGetDevice(&_cur));                                                                   \
+    VB_CHECK_ARG(_cur == (lay)->device, "current CUDA device %d is not the handle's device %d", _cur, (lay)->device); \
+  } while (0)
+
 // One step of the up (postorder) pass: combine children a and b into parent p.
 //   x = a | b<<16, y = p, z = slotA | slotB<<8 | slotOut<<16 (shared-memory slots; 0xff = none),
 //   w = flags: bit0 a is a tip, bit1 b is a tip, bit2 p is the root, bit3 a is the result of the previous

@@ -27,6 +27,7 @@ extern "C" int vbsky_session_create(const vbsky_layout* lay, const vbsky_tips* t
                                     vbsky_session** out) {
   VB_CHECK_ARG(lay && tips && out, "NULL argument");
   VB_CHECK_ARG(U_max >= 1 && m_max >= 0, "bad capacity U_max=%d m_max=%d", U_max, m_max);
+  VB_CHECK_DEVICE(lay);
   *out = nullptr;
   auto* s = new vbsky_session();
   s->lay = lay, s->tips = tips, s->U_max = U_max, s->m_max = m_max;

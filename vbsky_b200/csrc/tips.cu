@@ -160,7 +160,7 @@ extern "C" int vbsky_tips_create(const vbsky_layout* lay, int64_t S, const uint8
   VB_CHECK_ARG(out, "out is NULL");
   *out = nullptr;
   VB_CHECK_ARG(lay, "layout is NULL");
-  VB_CHECK_ARG(lay->device >= 0, "layout was created without a CUDA device; there is no CPU fallback");
+  VB_CHECK_DEVICE(lay);
   const int32_t T = lay->T, n = lay->n;
   VB_CHECK_ARG(S >= 1, "S must be >= 1 (got %lld)", (long long)S);
   VB_CHECK_ARG(patterns && counts, "NULL argument");
