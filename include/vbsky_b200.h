@@ -59,6 +59,9 @@ typedef struct vbsky_subst_model {
 int vbsky_hky(double kappa, vbsky_subst_model* out);
 /* Q = P diag(d) Pinv into q[16]. */
 int vbsky_subst_rate_matrix(const vbsky_subst_model* m, double* q);
+/* d(d)/d(kappa) for vbsky_hky's spectrum into dd[4].  The eigenvectors of HKY with uniform
+ * frequencies do not depend on kappa, so dQ/dkappa = P diag(dd) Pinv commutes with Q.        */
+int vbsky_hky_dkappa(double kappa, double* dd);
 
 /* ------------------------------------------------------------------------------------------
  * Tip encoding and site-pattern compression (host, bit-exact).
@@ -186,6 +189,18 @@ int vbsky_prune_value_and_grad_f32(const vbsky_layout* lay, const vbsky_tips* ti
                                    const int32_t* unit_tree, const double* bl,
                                    const vbsky_subst_model* model, double* site_ll, double* ll,
                                    double* dll_dbl, void* ws, size_t ws_bytes, void* stream);
+
+/* Gradient with respect to substitution parameters (asked for by the north star; the reference
+ * drops these tangents, prune.py:149).  Same evaluation as vbsky_prune_value_and_grad, but the
+ * quadratic form of eq. (9) uses G = P diag(g) Pinv instead of Q = P diag(d) Pinv:
+ *   out[u][b] = sum_s counts[s] * (pre_b^T G post_b) / L_s          (g = d gives dll_dbl).
+ * For a parameter theta that moves only the spectrum (dQ/dtheta = P diag(dd/dtheta) Pinv, e.g.
+ * kappa of vbsky_hky via vbsky_hky_dkappa), dP_b/dtheta = bl_b G P_b and therefore
+ *   d ll[u] / d theta = sum_b bl[u][b] * out[u][b].                                           */
+int vbsky_prune_spectral_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                              const int32_t* unit_tree, const double* bl,
+                              const vbsky_subst_model* model, const double* g, double* ll,
+                              double* out, void* ws, size_t ws_bytes, void* stream);
 
 /* Counters of the last prune call made by this thread: out[0]=kernel launches,
  * out[1]=persistent CTAs, out[2]=sites per CTA tile, out[3]=dynamic smem bytes per CTA,

@@ -233,3 +233,41 @@ def test_prune_loglik_reference_signature(cuda):
     np.testing.assert_allclose(tbl.grad.cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
     single = prune_loglik(torch.tensor(bl, device=cuda), Q, part[0], td)  # [n, 4] -> scalar, as in the reference
     assert single.dim() == 0 and abs(single.item() - want_ll[0]) <= LL_RTOL * abs(want_ll[0]) + LL_ATOL
+
+
+@pytest.mark.parametrize("T,n,S,K,kappa,clock", [(2, 10, 300, 2, 2.7, 0.05), (1, 63, 411, 2, 1.0, 0.01), (1, 200, 1000, 1, 4.0, 1.12e-3)])
+def test_kappa_gradient_matches_finite_differences(cuda, T, n, S, K, kappa, clock):
+    """d ll / d kappa (north star: gradient w.r.t. substitution parameters; the reference drops these tangents,
+    prune.py:149, so the pin is a central difference of the fp64 oracle and of the kernel's own value)."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, HKY_dkappa, codes_to_partials
+    from vbsky_b200.synth import make_ensemble
+
+    data = make_ensemble(T, n, S, K, seed=n + S, Q=HKY(kappa), clock_rate=clock, missing=0.05)
+    bl = np.stack([data.heights[t].branch_lengths[k] for t in range(T) for k in range(K)]) * data.clock_rate
+    unit_tree = np.repeat(np.arange(T, dtype=np.int32), K)
+    bl_d, ut_d = torch.as_tensor(bl, device=cuda), torch.as_tensor(unit_tree, device=cuda)
+    ens = Ensemble(data.tds, data.tips, HKY(kappa), device=cuda)
+    # g = d reproduces the branch-length gradient bit for bit
+    ll0, dll0, _ = ens.prune(bl_d, ut_d)
+    ll1, out1 = ens.prune_spectral_grad(bl_d, ut_d, HKY(kappa).d)
+    assert torch.equal(ll0, ll1) and torch.equal(dll0, out1)
+    got = ens.dll_dkappa(bl_d, ut_d, kappa).cpu().numpy()
+    ens.close()
+    h = 1e-4 * kappa
+    lls = []
+    for kk in (kappa + h, kappa - h):
+        e = Ensemble(data.tds, data.tips, HKY(kk), device=cuda)
+        lls.append(e.prune(bl_d, ut_d, want_grad=False)[0].cpu().numpy())
+        e.close()
+    fd_gpu = (lls[0] - lls[1]) / (2 * h)
+    scale = np.abs(got).max()
+    np.testing.assert_allclose(got, fd_gpu, rtol=1e-6, atol=1e-6 * scale)
+    # oracle central difference on the first unit
+    td = _oracle_td(data.tds[0])
+    part = codes_to_partials(data.tips[0].patterns)
+    f = lambda kk: oprune.data_loglik_and_grad(bl[0], osub.HKY(kk), part, data.tips[0].counts, td)[0]
+    fd_or = (f(kappa + h) - f(kappa - h)) / (2 * h)
+    assert got[0] == pytest.approx(fd_or, rel=1e-6, abs=1e-6 * scale)
+    # closed-form spectrum derivative vs a difference of the model's own eigenvalues
+    assert np.allclose(HKY_dkappa(kappa), (HKY(kappa + h).d - HKY(kappa - h).d) / (2 * h), rtol=1e-7, atol=1e-10)

@@ -59,6 +59,8 @@ SIGNATURES = {
     "vbsky_device_count": (C.c_int, []),
     "vbsky_hky": (C.c_int, [C.c_double, C.POINTER(SubstModel)]),
     "vbsky_subst_rate_matrix": (C.c_int, [C.POINTER(SubstModel), _f64p]),
+    "vbsky_hky_dkappa": (C.c_int, [C.c_double, _f64p]),
+    "vbsky_prune_spectral_grad": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _f64p, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vbsky_encode_tips": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _u8p]),
     "vbsky_compress_patterns": (C.c_int, [_u8p, C.c_int64, C.c_int64, _i64p, _u8p, _i64p, _i64p]),
     "vbsky_encode_tips_device": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _i64p, _vp]),

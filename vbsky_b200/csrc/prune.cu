@@ -173,6 +173,12 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
                                           double* dll_dbl, void* ws, size_t ws_bytes, void* stream) {
   return f64::run(lay, tips, U, unit_tree, bl, model, site_ll, ll, dll_dbl, ws, ws_bytes, stream);
 }
+extern "C" int vbsky_prune_spectral_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, const int32_t* unit_tree,
+                                         const double* bl, const vbsky_subst_model* model, const double* g, double* ll,
+                                         double* out, void* ws, size_t ws_bytes, void* stream) {
+  VB_CHECK_ARG(g && out, "NULL argument");
+  return f64::run(lay, tips, U, unit_tree, bl, model, nullptr, ll, out, ws, ws_bytes, stream, g);
+}
 extern "C" size_t vbsky_prune_workspace_bytes_f32(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, int32_t want_grad) {
   return f32::workspace_bytes(lay, tips, U, want_grad);
 }

@@ -34,6 +34,15 @@ extern "C" int vbsky_hky(double kappa, vbsky_subst_model* out) {
   return VBSKY_OK;
 }
 
+extern "C" int vbsky_hky_dkappa(double kappa, double* dd) {
+  VB_CHECK_ARG(dd, "dd is NULL");
+  VB_CHECK_ARG(kappa > 0 && std::isfinite(kappa), "kappa must be positive and finite (got %g)", kappa);
+  // d/dkappa of the spectrum above; the eigenvectors do not depend on kappa, so dQ/dkappa = P diag(dd) Pinv
+  const double s = 1.0 / ((2.0 + kappa) * (2.0 + kappa));
+  dd[0] = dd[1] = -2.0 * s, dd[2] = 4.0 * s, dd[3] = 0.0;
+  return VBSKY_OK;
+}
+
 extern "C" int vbsky_subst_rate_matrix(const vbsky_subst_model* m, double* q) {
   VB_CHECK_ARG(m && q, "NULL argument");
   for (int i = 0; i < 4; ++i)

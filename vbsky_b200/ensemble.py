@@ -133,6 +133,37 @@ class Ensemble:
                 _ptr(site), _ptr(ll), _ptr(dll), _ptr(ws), ws.numel(), C.c_void_p(stream)))
         return ll, dll, site
 
+    def prune_spectral_grad(self, bl: torch.Tensor, unit_tree: torch.Tensor, g):
+        """``vbsky_prune_spectral_grad``: returns (ll [U], out [U, 2n-2]) where ``out`` is eq. (9) with
+        G = P diag(g) Pinv in place of Q.  For a parameter that only moves the spectrum, d ll/d theta =
+        (bl * out).sum(1) with g = d d/d theta (``substitution.HKY_dkappa`` for kappa)."""
+        U = bl.shape[0]
+        if bl.dtype != torch.float64 or bl.device != self.device or bl.shape != (U, 2 * self.n - 2):
+            raise ValueError(f"bl must be a float64 [{U}, {2 * self.n - 2}] tensor on {self.device}")
+        if unit_tree.dtype != torch.int32 or unit_tree.device != self.device or unit_tree.shape != (U,):
+            raise ValueError("unit_tree must be an int32 [U] tensor on the ensemble's device")
+        g = np.ascontiguousarray(np.asarray(g, dtype=np.float64).reshape(4))
+        bl = bl.contiguous()
+        with torch.cuda.device(self.device):
+            need = _lib.lib.vbsky_prune_workspace_bytes(self._layout, self._tips, U, 1)
+            if need == 0:
+                raise _lib.VbskyError(-1, _lib.last_error())
+            ws = self._workspace(need)
+            ll = torch.empty(U, dtype=torch.float64, device=self.device)
+            out = torch.empty(U, 2 * self.n - 2, dtype=torch.float64, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib.vbsky_prune_spectral_grad(
+                self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model),
+                _lib.np_ptr(g, C.c_double), _ptr(ll), _ptr(out), _ptr(ws), ws.numel(), C.c_void_p(stream)))
+        return ll, out
+
+    def dll_dkappa(self, bl: torch.Tensor, unit_tree: torch.Tensor, kappa: float) -> torch.Tensor:
+        """d ll[u] / d kappa for an ensemble built with ``HKY(kappa)`` (one extra evaluation of the pruning kernel)."""
+        from .substitution import HKY_dkappa
+
+        _, out = self.prune_spectral_grad(bl, unit_tree, HKY_dkappa(kappa))
+        return (bl * out).sum(1)
+
     def prune_host(self, bl: np.ndarray, unit_tree: np.ndarray, ll_out: Optional[np.ndarray] = None,
                    dll_out: Optional[np.ndarray] = None, want_grad: bool = True):
         """Host-buffer call (vbsky_prune_value_and_grad_host): bl [U, 2n-2] float64 and unit_tree [U]

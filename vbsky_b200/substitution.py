@@ -45,6 +45,13 @@ def HKY(kappa: float = 1) -> SubstitutionModel:
     )
 
 
+def HKY_dkappa(kappa: float) -> np.ndarray:
+    """d(d)/d(kappa) of ``HKY(kappa)``'s spectrum [4]; dQ/dkappa = P diag(.) Pinv since the eigenvectors are fixed."""
+    dd = np.zeros(4)
+    _lib.check(_lib.lib.vbsky_hky_dkappa(float(kappa), _lib.np_ptr(dd, C.c_double)))
+    return dd
+
+
 def JC69() -> SubstitutionModel:
     return HKY(1.0)
 
