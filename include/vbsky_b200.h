@@ -301,6 +301,13 @@ int vbsky_local_flow_backward(int32_t U, int32_t d, const int32_t* unit_tree, co
                               const double* log_sigma, const double* eps, const double* dx,
                               const double* dlogq, double* dmu, double* dlog_sigma, void* stream);
 
+/* One optimiser step of SeqData.loop (fasta.py:388, 421-433) fused over a flat block of n
+ * variational parameters on the device: jax.example_libraries.optimizers.adagrad(step_size,
+ * momentum = 0.9 by default) on nan_to_num(g):  g_sq += g^2;
+ * m = (1 - momentum) g / sqrt(g_sq) + momentum m (0 where g_sq == 0);  x -= step_size m.       */
+int vbsky_adagrad_update(int64_t n, double* x, const double* g, double* g_sq, double* m,
+                         double step_size, double momentum, void* stream);
+
 /* CUDA-event timing of the fused pruning kernel alone (used for the roofline figure): after
  * vbsky_prune_timing(1, NULL, NULL) every prune call of this thread brackets the kernel with an
  * event pair on its stream; a later call drains them into *ms_sum / *launches (and sets the new

@@ -56,3 +56,29 @@ def test_alignment_to_fit_pipeline(cuda):
     hist = model.fit(n_iter=5, step_size=0.1)
     assert np.isfinite(hist).all()
     ens.close()
+
+
+def test_adagrad_kernel_matches_jax_rule(cuda):
+    """vbsky_adagrad_update vs the restated jax.example_libraries.optimizers.adagrad + nan_to_num (fasta.py:388,421-433)."""
+    import oracle.optim as ooptim
+    from vbsky_b200.optim import Adagrad
+
+    rng = np.random.default_rng(0)
+    n = 10007
+    x0 = rng.standard_normal(n)
+    x = torch.as_tensor(x0.copy(), device=cuda)
+    opt = Adagrad(x, step_size=0.7)
+    state = ooptim.adagrad_init(x0)
+    for it in range(6):
+        g = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8, n)
+        g[rng.random(n) < 0.01] = np.nan
+        g[rng.random(n) < 0.01] = np.inf
+        g[rng.random(n) < 0.01] = -np.inf
+        if it < 2:
+            g[:100] = 0.0  # g_sq stays 0 -> no update there
+        opt.update(torch.as_tensor(g, device=cuda))
+        state = ooptim.adagrad_update(g, state, 0.7)
+    assert np.array_equal(x.cpu().numpy(), state[0])
+    assert np.array_equal(opt.g_sq.cpu().numpy(), state[1])
+    assert np.array_equal(opt.m.cpu().numpy(), state[2])
+    assert np.array_equal(x.cpu().numpy()[:100] != x0[:100], np.ones(100, bool))  # moved once gradients appeared

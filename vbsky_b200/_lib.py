@@ -92,6 +92,7 @@ SIGNATURES = {
     "vbsky_prune_timing": (C.c_int, [C.c_int32, _f64p, _i64p]),
     "vbsky_local_flow_sample": (C.c_int, [C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vbsky_local_flow_backward": (C.c_int, [C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vbsky_adagrad_update": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp]),
     "vbsky_heights_forward": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vbsky_heights_backward": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                          C.POINTER(ParamGrads), _vp, C.c_size_t, _vp]),

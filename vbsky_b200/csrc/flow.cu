@@ -106,3 +106,35 @@ extern "C" int vbsky_local_flow_backward(int32_t U, int32_t d, const int32_t* un
   VB_CUDA(cudaGetLastError());
   return VBSKY_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Optimiser step of SeqData.loop (fasta.py:388, 421-433): jax.example_libraries.optimizers.adagrad
+// (step_size, momentum = 0.9) applied to nan_to_num(g), fused over a flat parameter block:
+//   g_sq += g^2;  m = (1 - momentum) * g * (g_sq > 0 ? 1/sqrt(g_sq) : 0) + momentum * m;  x -= step_size * m.
+// jax (absent from this image) is restated from its published source.
+namespace vbsky {
+__global__ void adagrad_kernel(long long n, double* __restrict__ x, const double* __restrict__ g, double* __restrict__ g_sq,
+                               double* __restrict__ m, double step_size, double momentum) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double gi = g[i];
+    // jnp.nan_to_num: nan -> 0, +-inf -> +-largest finite
+    if (gi != gi) gi = 0.0;
+    else if (isinf(gi)) gi = gi > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    const double acc = __dadd_rn(g_sq[i], __dmul_rn(gi, gi));
+    const double inv = acc > 0 ? 1.0 / sqrt(acc) : 0.0;
+    const double mi = __dadd_rn(__dmul_rn(1.0 - momentum, __dmul_rn(gi, inv)), __dmul_rn(momentum, m[i]));
+    g_sq[i] = acc, m[i] = mi;
+    x[i] = __dsub_rn(x[i], __dmul_rn(step_size, mi));
+  }
+}
+}  // namespace vbsky
+
+extern "C" int vbsky_adagrad_update(int64_t n, double* x, const double* g, double* g_sq, double* m, double step_size,
+                                    double momentum, void* stream) {
+  VB_CHECK_ARG(n >= 0 && (n == 0 || (x && g && g_sq && m)), "NULL argument");
+  if (n == 0) return VBSKY_OK;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  vbsky::adagrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, x, g, g_sq, m, step_size, momentum);
+  VB_CUDA(cudaGetLastError());
+  return VBSKY_OK;
+}

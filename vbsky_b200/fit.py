@@ -19,6 +19,7 @@ import torch
 from . import bdsky
 from .ensemble import Ensemble
 from .flows import local_flow
+from .optim import Adagrad
 
 
 def _pos_sample(p: Dict[str, torch.Tensor], eps: torch.Tensor):
@@ -41,29 +42,37 @@ class EnsembleELBO:
         self.prior_fn = prior_fn
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)
-        z = lambda *shape: torch.zeros(*shape, dtype=torch.float64, device=dev)
-        # variational parameters (the reference initialises them with N(0, 0.1); fasta.py:439-446)
-        self.params = {
-            "origin": {"mu": z(1), "log_sigma": z(1)},
-            "R": {"mu": z(m), "log_sigma": z(m)},
-            "local": {"mu": z(T, n - 1), "log_sigma": z(T, n - 1)},  # [proportions (n-2), root_proportion]
-        }
-        for grp in self.params.values():
-            for k, v in grp.items():
-                v.copy_(0.1 * torch.randn(v.shape, dtype=torch.float64, device=dev, generator=self.gen))
-                v.requires_grad_(True)
+        # variational parameters live in one flat leaf so that a single fused kernel updates them
+        # (the reference initialises them with N(0, 0.1); fasta.py:439-446)
+        self._shapes = {"origin": (1,), "R": (m,), "local": (T, n - 1)}  # local = [proportions (n-2), root_proportion]
+        total = 2 * sum(math.prod(sh) for sh in self._shapes.values())
+        self.theta = 0.1 * torch.randn(total, dtype=torch.float64, device=dev, generator=self.gen)
+        self.theta.requires_grad_(True)
+
+    @property
+    def params(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        """Views of the flat parameter block: {flow: {"mu", "log_sigma"}}."""
+        out, off = {}, 0
+        for name, sh in self._shapes.items():
+            out[name] = {}
+            for k in ("mu", "log_sigma"):
+                cnt = math.prod(sh)
+                out[name][k] = self.theta[off : off + cnt].view(sh)
+                off += cnt
+        return out
 
     def leaves(self):
-        return [v for grp in self.params.values() for v in grp.values()]
+        return [self.theta]
 
     def elbo(self) -> torch.Tensor:
         ens, K, m = self.ens, self.K, self.m
         T, n, dev = ens.T, ens.n, ens.device
         U = T * K
         rnd = lambda *shape: torch.randn(*shape, dtype=torch.float64, device=dev, generator=self.gen)
-        origin, lq_o = _pos_sample(self.params["origin"], rnd(K, 1))
-        R, lq_r = _pos_sample(self.params["R"], rnd(K, m))
-        x, lq_local = local_flow(self.params["local"]["mu"], self.params["local"]["log_sigma"], rnd(U, n - 1), self.unit_tree)
+        par = self.params
+        origin, lq_o = _pos_sample(par["origin"], rnd(K, 1))
+        R, lq_r = _pos_sample(par["R"], rnd(K, m))
+        x, lq_local = local_flow(par["local"]["mu"], par["local"]["log_sigma"], rnd(U, n - 1), self.unit_tree)
         ks = torch.arange(K, device=dev).repeat(T)  # sample index of each unit
         full = lambda v: torch.full((U, m), v, dtype=torch.float64, device=dev)
         p = {
@@ -80,18 +89,16 @@ class EnsembleELBO:
         return val
 
     def fit(self, n_iter: int = 10, step_size: float = 1.0, callback=None):
-        """Adagrad on -ELBO (jax.example_libraries.optimizers.adagrad of fasta.py:388: x -= lr * g / sqrt(sum g^2),
-        momentum 0.9 on the squared-gradient accumulator is the library default there; torch's Adagrad is the
-        plain accumulator)."""
-        opt = torch.optim.Adagrad(self.leaves(), lr=step_size)
+        """The loop of SeqData.loop on -ELBO (fasta.py:387-487): gradients cleaned with nan_to_num (:421,427) and
+        jax.example_libraries.optimizers.adagrad(step_size) -- momentum 0.9 on the normalised gradient -- applied to
+        every variational parameter by one fused kernel (``vbsky_adagrad_update``)."""
+        opt = Adagrad(self.theta.data, step_size=step_size)
         hist = []
         for i in range(n_iter):
-            opt.zero_grad(set_to_none=True)
+            self.theta.grad = None
             loss = -self.elbo()
             loss.backward()
-            for v in self.leaves():
-                v.grad.nan_to_num_()  # fasta.py:421,427
-            opt.step()
+            opt.update(self.theta.grad)
             hist.append(loss.item())
             if callback:
                 callback(i, loss.item())
