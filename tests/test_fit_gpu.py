@@ -108,3 +108,14 @@ def test_sequential_fit_follows_reference_schedule(cuda):
     last = np.mean([[-model.elbo(trees=[j]).item() for j in range(T)] for _ in range(4)], axis=0)
     assert (last < first).all(), (first, last)
     ens.close()
+
+
+def test_hcv_example_runs(cuda):
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("hcv_fit", os.path.join(os.path.dirname(__file__), "..", "examples", "hcv_fit.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    hist, R_mean = mod.main(n_trees=4, n_tips=10, n_iter=12, verbose=False)
+    assert np.isfinite(hist).all() and np.isfinite(R_mean).all() and np.mean(hist[-3:]) < np.mean(hist[:3])
