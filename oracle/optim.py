@@ -11,8 +11,8 @@ def adagrad_init(x0):
 def adagrad_update(g, state, step_size, momentum=0.9):
     x, g_sq, m = state
     g = np.nan_to_num(np.asarray(g, dtype=np.float64))  # fasta.py:421,427
-    g_sq = g_sq + np.square(g)
-    with np.errstate(divide="ignore"):
+    with np.errstate(divide="ignore", over="ignore"):
+        g_sq = g_sq + np.square(g)
         g_sq_inv_sqrt = np.where(g_sq > 0, 1.0 / np.sqrt(g_sq), 0.0)
     m = (1.0 - momentum) * (g * g_sq_inv_sqrt) + momentum * m
     x = x - step_size * m
