@@ -109,7 +109,7 @@ int vbsky_compress_patterns_device(int32_t T, int64_t L, int32_t n, const uint8_
  * overwritten): merges dev [T][n-1][2] = (clade1, clade2) of the k-th inner clade in child
  * order, a clade being a tip position < n or n + (index of an earlier merge); heights dev
  * [T][n-1] = min_dist / 2.  Ties are broken as Biopython's scan does (last `>=` hit); the new
- * row is the plain average of the two merged rows.  n <= 1024.                                */
+ * row is the plain average of the two merged rows.  n <= 4096.                                */
 size_t vbsky_snp_planes_bytes(int64_t N, int64_t L);
 int vbsky_snp_pack_device(const char* seqs, int64_t N, int64_t L, uint32_t* planes, void* stream);
 int vbsky_snp_dists_device(const uint32_t* planes, int64_t N, int64_t L, const int32_t* rows,

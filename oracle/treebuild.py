@@ -131,3 +131,34 @@ def nested_to_newick(tree) -> str:
             return "(" + ",".join(f(c) for c in t) + ")"
         return str(t)
     return f(tree) + ";"
+
+
+def upgma_vectorised(mat: np.ndarray):
+    """Same merges and heights as ``upgma`` (checked against it in tests/test_treebuild_oracle.py) with NumPy doing each
+    round's scan: live clades keep their relative order, so Biopython's positions are the live slots in ascending order
+    and its last ``>=`` hit is the last minimum in row-major order over the live lower triangle.  For n in the thousands,
+    where the literal list-of-lists loop is too slow to run in a test."""
+    n = mat.shape[0]
+    D = np.tril(np.asarray(mat, dtype=np.float64), -1)
+    D = D + D.T
+    alive = np.arange(n)
+    cid = np.arange(n)
+    merges, heights = [], []
+    for rnd in range(n - 1):
+        sub = D[np.ix_(alive, alive)]
+        m = len(alive)
+        r, c = np.tril_indices(m, -1)
+        vals = sub[r, c]
+        k = np.flatnonzero(vals == vals.min())[-1]
+        pi, pj = r[k], c[k]
+        i, j = alive[pi], alive[pj]
+        d = vals[k]
+        merges.append((cid[i], cid[j]))
+        heights.append(d * 1.0 / 2)
+        others = alive[(alive != i) & (alive != j)]
+        new = (D[i, others] + D[j, others]) * 1.0 / 2
+        D[j, others] = new
+        D[others, j] = new
+        cid[j] = n + rnd
+        alive = np.delete(alive, pi)
+    return np.array(merges, dtype=np.int32).reshape(-1, 2), np.array(heights)

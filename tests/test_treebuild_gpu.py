@@ -109,6 +109,20 @@ def test_upgma_bit_exact(cuda, n, kind):
         assert np.array_equal(heights[t], h)
 
 
+def test_upgma_beyond_one_position_per_thread(cuda):
+    """n > 1024 tips (several live positions per thread) with integer distances, i.e. many exact ties."""
+    from vbsky_b200.treebuild import upgma
+
+    rng = np.random.default_rng(3)
+    n = 1500
+    D = np.tril(rng.integers(0, 40, (n, n)).astype(float), -1)
+    D = D + D.T
+    merges, heights = upgma(torch.as_tensor(D[None], device=cuda))
+    m, h = otb.upgma_vectorised(D)
+    assert np.array_equal(merges[0].cpu().numpy(), m)
+    assert np.array_equal(heights[0].cpu().numpy(), h)
+
+
 @pytest.mark.parametrize("kind", ["distinct", "equal"])
 def test_sample_trees_match_reference_chain(cuda, kind):
     """alignment -> snp-dists -> sUPGMA correction -> UPGMA -> Newick -> TreeData.from_newick (+ sample times)."""

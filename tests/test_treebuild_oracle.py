@@ -77,3 +77,20 @@ def test_upgma_is_a_valid_monotone_clustering():
     assert sorted(merges.reshape(-1).tolist()) == list(range(2 * n - 2))  # every clade is used exactly once
     assert all(max(m) < n + k for k, m in enumerate(merges))
     assert np.all(np.diff(heights) >= -1e-12)
+
+
+@pytest.mark.parametrize("kind", ["float", "int", "ties"])
+def test_vectorised_upgma_equals_literal_loop(kind):
+    rng = np.random.default_rng(5)
+    n = 37
+    if kind == "float":
+        x = rng.random((n, 3))
+        D = np.linalg.norm(x[:, None] - x[None], axis=-1)
+    elif kind == "int":
+        D = rng.integers(0, 5, (n, n)).astype(float)
+    else:
+        D = np.ones((n, n))
+    D = np.tril(D, -1)
+    m1, h1, _ = otb.upgma(D)
+    m2, h2 = otb.upgma_vectorised(D)
+    assert np.array_equal(m1, m2) and np.array_equal(h1, h2)

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) snp_dists_kernel(const uint32_t* __restri
 }
 
 constexpr int TB = 1024;
+constexpr int kUpgmaPosPerThread = 4;  // upgma_kernel handles n <= 4 * TB tips
 
 // Sum of v over the CTA in a fixed order (thread-id tree), result broadcast.
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -235,11 +236,17 @@ __global__ void __launch_bounds__(TB) upgma_kernel(const UpgmaParams p) {
       }
     }
     __syncthreads();
-    // retire slot i: shift the tail of the (ascending) position list down by one; n <= TB so one position per thread
-    int nv = -1;
-    if (tid < m - 1 && alive[tid] >= i) nv = alive[tid + 1];
+    // retire slot i: shift the tail of the (ascending) position list down by one (read everything, then write)
+    int nv[kUpgmaPosPerThread];
+#pragma unroll
+    for (int k = 0; k < kUpgmaPosPerThread; ++k) {
+      const int a = tid + k * TB;
+      nv[k] = (a < m - 1 && alive[a] >= i) ? alive[a + 1] : -1;
+    }
     __syncthreads();
-    if (nv >= 0) alive[tid] = nv;
+#pragma unroll
+    for (int k = 0; k < kUpgmaPosPerThread; ++k)
+      if (nv[k] >= 0) alive[tid + k * TB] = nv[k];
     if (tid == 0) cid[j] = n + round;
     __syncthreads();
   }
@@ -293,7 +300,7 @@ extern "C" int vbsky_supgma_distances_device(int32_t T, int32_t n, const int32_t
 
 extern "C" int vbsky_upgma_device(int32_t T, int32_t n, double* D, int32_t* merges, double* heights, void* stream) {
   VB_CHECK_ARG(D && merges && heights, "NULL argument");
-  VB_CHECK_ARG(T >= 1 && n >= 2 && n <= TB, "bad shape T=%d n=%d (n <= %d)", T, n, TB);
+  VB_CHECK_ARG(T >= 1 && n >= 2 && n <= kUpgmaPosPerThread * TB, "bad shape T=%d n=%d (n <= %d)", T, n, kUpgmaPosPerThread * TB);
   UpgmaParams p{D, merges, heights, n};
   upgma_kernel<<<T, TB, (size_t)2 * n * sizeof(int), (cudaStream_t)stream>>>(p);
   VB_CUDA(cudaGetLastError());
