@@ -37,6 +37,31 @@ def test_error_reporting_never_throws():
     assert _lib.lib.vbsky_version() >= 100
 
 
+def test_argument_checks_run_before_any_device_work():
+    """Bad shapes and NULL pointers are refused with VBSKY_EINVAL and a message, also on a box without a GPU."""
+    import ctypes as C
+
+    import numpy as np
+
+    from vbsky_b200 import _lib
+
+    L = _lib.lib
+    dd = np.zeros(4)
+    assert L.vbsky_hky_dkappa(0.0, _lib.np_ptr(dd, C.c_double)) == -1 and "kappa" in _lib.last_error()
+    assert L.vbsky_hky_dkappa(2.7, None) == -1
+    assert L.vbsky_hky_dkappa(2.7, _lib.np_ptr(dd, C.c_double)) == 0
+    s = 1.0 / (4.7 * 4.7)
+    assert np.allclose(dd, [-2 * s, -2 * s, 4 * s, 0.0], rtol=1e-15)
+    assert L.vbsky_adagrad_update(5, None, None, None, None, 1.0, 0.9, None) == -1
+    assert L.vbsky_adagrad_update(0, None, None, None, None, 1.0, 0.9, None) == 0
+    assert L.vbsky_upgma_device(1, 1, None, None, None, None) == -1
+    assert L.vbsky_upgma_device(1, 5000, C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), None) == -1 and "4096" in _lib.last_error()
+    assert L.vbsky_supgma_distances_device(0, 4, None, None, 0, None, None, None) == -1
+    assert L.vbsky_snp_dists_device(None, 1, 1, None, 1, 2, None, None) == -1
+    assert L.vbsky_snp_planes_bytes(3, 33) == 3 * 4 * 2 * 4
+    assert L.vbsky_prune_spectral_grad(None, None, 1, None, None, None, None, None, None, None, 0, None) == -1
+
+
 def test_no_product_import_of_oracle():
     """The product package must never import the oracle (it is test infrastructure)."""
     pkg = os.path.join(ROOT, "vbsky_b200")
