@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--trees", type=int, default=0, help="override T (development only; marks the line as reduced)")
     ap.add_argument("--cpu-sample-units", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compress", action="store_true",
+                    help="merge identical site columns per tree first (np.unique semantics, on the device) as prep_data does; "
+                         "not the BASELINE configuration, which uses every site as a pattern")
     return ap.parse_args()
 
 
@@ -183,6 +186,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     data, T, n, S, K, clock = build_workload(args, device=dev)
+    sites = S
+    if args.compress:
+        from vbsky_b200.tips import PackedTips, compress_patterns_device, pad_tips
+
+        packed = compress_patterns_device(torch.as_tensor(np.stack([tp.patterns for tp in data.tips]), device=dev))
+        data = data._replace(tips=pad_tips([PackedTips(p.cpu().numpy(), c.cpu().numpy().astype(np.float64)) for p, c in packed]))
+        S = int(data.tips[0].patterns.shape[0])
     Q = HKY(KAPPA)
     ens = Ensemble(data.tds, data.tips, Q, device=dev)
     # (tree, sample) units, round-robin over ranks
@@ -298,6 +308,8 @@ def main():
             "sharding": f"{T * K} units round-robin over {world} rank(s); one all-reduce of [ELBO, d/d global params] ({1 + 2 + 4 * M_INTERVALS} doubles) per step",
             "l2": "working set per step (message scratch + step tables, > 500 MB) exceeds the 126 MB L2; no explicit flush",
             "reduced": bool(args.trees),
+            **({"patterns": f"{sites} sites per tree compressed on the device to at most {S} unique site patterns (padded to the ensemble maximum)"}
+               if args.compress else {}),
         },
         "e2e": {"value": 1e3 / e2e_ms.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "vbsky_loglik_value_and_grad_host: pinned host parameters in, ll + all gradients out, per step; tip codes resident (uploaded once, as prep_data is one-off in the reference)"},
@@ -308,7 +320,7 @@ def main():
             "frac": achieved / peak, "peak_source": peak_src,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r1_prune_kernel_bench_ncu_summary.txt
             # (one ncu --set full capture of this workload on one GPU); null for any other workload
-            "traffic": NCU_DRAM_BYTES_CONFIG3 if (args.workload == "config3" and world == 1 and not args.trees) else None,
+            "traffic": NCU_DRAM_BYTES_CONFIG3 if (args.workload == "config3" and world == 1 and not args.trees and not args.compress) else None,
             "algorithmic_bytes_per_launch": stats["algorithmic_bytes"], "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
         },
     }
