@@ -66,6 +66,68 @@ def test_prune_matches_oracle(cuda, T, n, S, K, kappa, clock):
     _check(data, kappa, cuda, K)
 
 
+def _gtr(rng):
+    """A general time-reversible model with non-uniform frequencies as a (pi, P, d, Pinv) tuple: the dense matrix path."""
+    pi = rng.dirichlet(np.full(4, 5.0))
+    S = np.triu(rng.uniform(0.2, 2.0, (4, 4)), 1)
+    S = S + S.T
+    Q = S * pi[None, :]
+    np.fill_diagonal(Q, -Q.sum(1))
+    Q /= -(pi * np.diag(Q)).sum()
+    sq = np.sqrt(pi)
+    d, V = np.linalg.eigh(sq[:, None] * Q / sq[None, :])  # symmetrised; eigenvectors orthonormal
+    return pi, V / sq[:, None], d, V.T * sq[None, :]
+
+
+@pytest.mark.parametrize("T,n,S,K", [(2, 9, 300, 2), (1, 120, 700, 2)])
+def test_prune_general_model_dense_matrices(cuda, T, n, S, K):
+    """Non-K80 models take the dense 4x4 path (HKY/JC69 take the structured one): parity with the oracle."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, SubstitutionModel, codes_to_partials
+    from vbsky_b200.synth import make_ensemble
+
+    rng = np.random.default_rng(n)
+    pi, P, d, Pinv = _gtr(rng)
+    Q, oQ = SubstitutionModel(pi, P, d, Pinv), osub.SubstitutionModel(pi, P, d, Pinv)
+    assert np.allclose(Q.Q.sum(1), 0, atol=1e-12) and np.allclose(pi @ Q.Q, 0, atol=1e-12)
+    data = make_ensemble(T, n, S, K, seed=n + S, Q=HKY(2.0), clock_rate=0.05, missing=0.05)
+    ens = Ensemble(data.tds, data.tips, Q, device=cuda)
+    bl = np.stack([data.heights[t].branch_lengths[k] for t in range(T) for k in range(K)]) * 0.05
+    ut = np.repeat(np.arange(T, dtype=np.int32), K)
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), torch.as_tensor(ut, device=cuda), want_site_ll=True)
+    ll, dll, site = ll.cpu().numpy(), dll.cpu().numpy(), site.cpu().numpy()
+    ens.close()
+    for u in range(T * K):
+        t = ut[u]
+        tot, g, sll = oprune.data_loglik_and_grad(bl[u], oQ, codes_to_partials(data.tips[t].patterns), data.tips[t].counts, _oracle_td(data.tds[t]))
+        np.testing.assert_allclose(site[u], sll, rtol=LL_RTOL, atol=LL_ATOL)
+        np.testing.assert_allclose(ll[u], tot, rtol=LL_RTOL)
+        np.testing.assert_allclose(dll[u], g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+
+
+def test_structured_and_dense_matrix_paths_agree(cuda, monkeypatch):
+    """HKY through the K80-structured matrices vs the same model forced through the dense path."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY
+    from vbsky_b200.synth import make_ensemble
+
+    data = make_ensemble(2, 40, 900, 2, seed=4, Q=HKY(2.7), clock_rate=0.02, missing=0.05)
+    ens = Ensemble(data.tds, data.tips, HKY(2.7), device=cuda)
+    bl = np.stack([data.heights[t].branch_lengths[k] for t in range(2) for k in range(2)]) * 0.02
+    bl[1, 3] = 0.0  # one unit through the literal-clip variant
+    bl_d = torch.as_tensor(bl, device=cuda)
+    ut = torch.as_tensor(np.repeat(np.arange(2, dtype=np.int32), 2), device=cuda)
+    a = ens.prune(bl_d, ut, want_site_ll=True)
+    monkeypatch.setenv("VBSKY_DENSE_MATRICES", "1")
+    b = ens.prune(bl_d, ut, want_site_ll=True)
+    monkeypatch.delenv("VBSKY_DENSE_MATRICES")
+    ens.close()
+    assert not torch.equal(a[1], b[1])  # different arithmetic ...
+    for x, y, tol in ((a[0], b[0], 1e-12), (a[2], b[2], 1e-11), (a[1], b[1], 1e-9)):  # ... same numbers
+        x, y = x.cpu().numpy(), y.cpu().numpy()
+        assert np.max(np.abs(x - y)) <= tol * max(1.0, np.abs(y).max())
+
+
 def test_prune_compressed_patterns_and_padding(cuda):
     from vbsky_b200.substitution import HKY
     from vbsky_b200.synth import make_ensemble
