@@ -33,6 +33,7 @@
 //     staging buffer, written as per-tile partials and summed in a fixed order by finalize_kernel
 //     (bitwise reproducible).
 #include <cmath>
+#include <type_traits>
 
 #include "common.h"
 
