@@ -138,7 +138,12 @@ __device__ __forceinline__ real rcp_pos(real x) {
 __device__ __forceinline__ int exponent_of(real x) { return (__double2hiint(x) >> 20) - 1023; }
 __device__ __forceinline__ real scale_pow2(real x, int e) { return __hiloint2double(__double2hiint(x) - (e << 20), __double2loint(x)); }
 // messages stay unnormalised until their magnitude has drifted below 2^-256 (a step shrinks it by <= ~2^-133)
-__device__ __forceinline__ bool needs_rescale(real c) { return __double2hiint(c) < ((1023 - 256) << 20); }
+// (the magnitude of a positive vector is judged by the largest high word of its entries: integer max, no FP64 adds)
+__device__ __forceinline__ int mag_key(const real (&x)[4]) {
+  return max(max(__double2hiint(x[0]), __double2hiint(x[1])), max(__double2hiint(x[2]), __double2hiint(x[3])));
+}
+__device__ __forceinline__ bool key_needs_rescale(int key) { return key < ((1023 - 256) << 20); }
+__device__ __forceinline__ int key_exponent(int key) { return (key >> 20) - 1023; }
 #include "prune_impl.inc"
 }  // namespace f64
 
@@ -157,7 +162,11 @@ __device__ __forceinline__ real clip_literal(real x) { return fminf(fmaxf(x, 1e-
 __device__ __forceinline__ real rcp_pos(real x) { return __frcp_rn(x); }
 __device__ __forceinline__ int exponent_of(real x) { return (__float_as_int(x) >> 23) - 127; }
 __device__ __forceinline__ real scale_pow2(real x, int e) { return __int_as_float(__float_as_int(x) - (e << 23)); }
-__device__ __forceinline__ bool needs_rescale(real) { return true; }
+__device__ __forceinline__ int mag_key(const real (&x)[4]) {
+  return max(max(__float_as_int(x[0]), __float_as_int(x[1])), max(__float_as_int(x[2]), __float_as_int(x[3])));
+}
+__device__ __forceinline__ bool key_needs_rescale(int) { return true; }
+__device__ __forceinline__ int key_exponent(int key) { return (key >> 23) - 127; }
 #include "prune_impl.inc"
 }  // namespace f32
 
