@@ -171,11 +171,13 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
     up_row = {int(par): i for i, (_, par, _, _) in enumerate(up)}
     g = np.zeros((S, 2 * n - 2))
     Qm = Q.Q
+    carry = np.tile(Q.pi, (S, 1))  # pre[root] = pi seeds the carry; the root step is flagged "carried"
     for step, (x, par, z, w) in enumerate(down):
         a, b = x & 0xFFFF, (x >> 16) & 0xFFFF
         assert dn[2 * step] == a and dn[2 * step + 1] == b
         sp = z & 0xFF
-        pre = carry.copy() if w & 8 else (np.tile(Q.pi, (S, 1)) if sp == 0xFF else stack[sp].copy())
+        assert (w & 8) or sp != 0xFF
+        pre = carry.copy() if w & 8 else stack[sp].copy()
         assert not np.isnan(pre).any()
         carry = np.full((S, 4), np.nan)
         ma = Q.expm_action(bl[a], partials[:, a]) if w & 1 else scratch[up_row[a]]

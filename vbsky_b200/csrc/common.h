@@ -44,7 +44,7 @@ int set_error(int code, const char* fmt, ...);
 //   also be parked in slotOut.  The message produced by step s is streamed to scratch row s.
 // One step of the down (preorder) pass: expand parent p into children a and b.
 //   x = a | b<<16, y = p, z = slotP | 0xff<<8 | slotB<<16, w = flags: bit0/bit1 tips as above,
-//   bit3 pre_p is carried in registers from the previous step (else slotP, or pi for the root).
+//   bit3 pre_p is carried in registers from the previous step -- for the root step, from the seed pi -- (else slotP).
 //   The children are ordered so that an internal a is expanded by the next step (its pre vector is
 //   carried) and an internal b is parked in slotB until the walk returns to it.
 //   Internal children's messages arrive through the message ring in the order a, b (h_msg_rows).

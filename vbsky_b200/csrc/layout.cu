@@ -186,7 +186,7 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
       const int next = s + 1 < n - 1 ? dorder[s + 1] : -1;
       int sp = 0xff, sa = 0xff, sb = 0xff, flags = 0;
       if (v == root) {
-        // pre[root] = pi
+        flags |= 8;  // pre[root] = pi: the consumer seeds the carry registers with it before the walk
       } else if (s > 0 && parent[v] == dorder[s - 1]) {
         flags |= 8;  // carried in registers from the previous step
       } else {
