@@ -34,7 +34,7 @@ WORKLOADS = {
 }
 KAPPA = 2.7
 M_INTERVALS = 50  # skyline intervals (paper/covid.py m=50)
-NCU_DRAM_BYTES_CONFIG3 = 203.853908e9 + 191.174892e9  # dram read + write of prune_kernel<1,0,1>, profiles/r1_prune_kernel_bench_ncu_summary.txt
+NCU_DRAM_BYTES_CONFIG3 = 204.845845e9 + 191.205230e9  # dram read + write of prune_kernel<1,0,1>, profiles/r1_prune_kernel_bench_ncu_summary.txt
 UNIT = "ELBO+grad evals/s"
 METRIC = "elbo_grad_evals_per_sec"
 
