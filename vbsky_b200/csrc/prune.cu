@@ -46,7 +46,7 @@ constexpr int NCW = CT / 32;          // consumer warps
 constexpr int THREADS = CT + 32;      // + producer warp
 constexpr int CH = kChunkSteps;       // steps per ring stage
 constexpr int NST = 2;                // step-chunk ring stages
-constexpr int NMS_MAX = 3;            // message ring slots available; prune_config uses the third when it costs no resident CTA
+constexpr int NMS_MAX = 4;            // message ring slots available; prune_config uses the third when it costs no resident CTA
 constexpr int CODE_ROW = TILE;        // bytes of tip codes per (step, child)
 constexpr int GCH = 8;                // branch gradients staged per reduction round
 constexpr int GROW = 33;              // per-warp staging row: one value per lane (its two sites pre-added) + pad
