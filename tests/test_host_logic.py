@@ -177,6 +177,7 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
         assert dn[2 * step] == a and dn[2 * step + 1] == b
         sp = z & 0xFF
         assert (w & 8) or sp != 0xFF
+        assert (w & 3) != 1  # canonical order: a lone internal child is always child a (the kernel relies on it)
         pre = carry.copy() if w & 8 else stack[sp].copy()
         assert not np.isnan(pre).any()
         carry = np.full((S, 4), np.nan)
