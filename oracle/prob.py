@@ -42,3 +42,27 @@ def z1_log_pdf(params, x):
     base = (-0.5 * x0 * x0 - 0.5 * math.log(2 * math.pi)).sum(-1)
     ldj = params["log_sigma"].sum() + zero_one_log_det_jac(diagonal_affine_direct(params, x0))
     return base - ldj
+
+
+# ---- Transform(dim, Compose(DiagonalAffine, Exp)) = the reference's ``pos`` family (fasta.py:61, transform.py:152-166)
+def norm_logpdf(x):
+    """jax.scipy.stats.norm.logpdf with loc 0, scale 1: -(log(2 pi) + x^2) / 2."""
+    return (math.log(2 * math.pi) + x * x) / -2
+
+
+def pos_sample(params, eps):
+    return torch.exp(diagonal_affine_direct(params, eps))  # transform.py:158-159
+
+
+def pos_log_pdf(params, x):
+    """TransformedDistribution.log_pdf (transform.py:56-63) for Compose(DiagonalAffine, Exp)."""
+    x0 = diagonal_affine_inverse(params, torch.log(x))  # transform.py:164-166, 147-148
+    base = norm_logpdf(x0).sum(-1)  # distribution.py:63-65
+    ldj = params["log_sigma"].sum() + diagonal_affine_direct(params, x0).sum(-1)  # transform.py:144-145, 161-162
+    return base - ldj
+
+
+def constant_log_pdf(c, x):
+    """Constant.log_pdf (distribution.py:122-123)."""
+    close = (x - c).abs() <= 1e-8 + 1e-5 * c.abs()
+    return torch.where(close, torch.zeros_like(x), torch.full_like(x, -math.inf)).sum()

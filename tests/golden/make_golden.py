@@ -1,37 +1,65 @@
-"""Generates the committed fixtures under tests/golden/ from the reference's own example data
-(/root/reference/example/hcv.nexus, /root/reference/paper/sims/*/xmls/sim1.xml).  Run in the build
-container (where /root/reference is mounted); the GPU box only reads the JSON files.
+"""Generates the committed fixtures under tests/golden/ by EXECUTING THE REFERENCE'S OWN SOURCE on the reference's own
+example data (/root/reference/example/hcv.nexus, /root/reference/paper/sims/*/xmls/sim1.xml).
 
-The reference's JAX code cannot be imported here (no jax / msprime / tskit / Bio wheels, no network), so the
-expected values are produced by the oracle (oracle/, a line-by-line CPU restatement of the reference) and
-by plain NumPy calls that ARE the reference's statements (np.unique for pattern compression)."""
+Run in the build container, where /root/reference is mounted:  python tests/golden/make_golden.py
+The GPU box has no /root/reference and only reads the JSON files.
+
+How the numbers are produced: ``oracle/refshim`` imports the unmodified /root/reference/vbsky/*.py on a torch-fp64
+stand-in for the JAX subset they use (JAX itself cannot be installed here), so every expected value below is the output
+of the reference's functions -- ``TreeData.from_newick``, ``fasta._process_tips`` / ``SeqData.pad_tips``,
+``prune.prune_loglik`` + its custom JVP, ``bdsky.loglik`` under ``value_and_grad``, ``optim.loss`` under
+``value_and_grad`` and ``SeqData.loop`` -- not of a restatement.  The oracle (oracle/*.py) is asserted equal to each of
+them (<= 1e-12) before anything is written.  Fixtures say so in their ``generated_by`` field.
+
+Not the reference's: JAX's PRNG stream (the base draws are recorded and stored in the fixture instead), the starting
+trees (the reference shells out to ``snp-dists`` and Biopython's UPGMA, both absent; trees come from the oracle's
+restated UPGMA or a deterministic ladder -- any binary topology is a valid input to the path under test).
+"""
 import json
+import math
 import os
 import re
 import sys
+from types import SimpleNamespace
 
 import numpy as np
+import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import oracle.bdsky as obdsky  # noqa: E402
+import oracle.optim as oopt  # noqa: E402
 import oracle.prune as oprune  # noqa: E402
 import oracle.substitution as osub  # noqa: E402
 import oracle.tips as otips  # noqa: E402
 import oracle.tree_data as otd  # noqa: E402
+import oracle.treebuild as otb  # noqa: E402
+from oracle import refshim  # noqa: E402
+from oracle.util import TipData  # noqa: E402
 
 REF = "/root/reference"
+GENERATED_BY = ("reference source (/root/reference/vbsky/*.py, unmodified) executed under oracle/refshim "
+                "(torch-fp64 stand-in for the JAX subset); oracle asserted equal <= 1e-12 at generation time")
+ref = refshim.load_reference()
+jnp, jax = ref.jnp, ref.jax
+
+
+def _close(a, b, rtol=1e-12, what=""):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+    assert err <= rtol, (what, err)
 
 
 def hcv():
     names, seqs = otips.read_nexus_matrix(os.path.join(REF, "example", "hcv.nexus"))
     assert len(names) == 63 and all(len(s) == 411 for s in seqs)
-    part = np.array([osub.encode_partials(s) for s in seqs]).transpose(1, 0, 2)
-    pat, cnt = np.unique(part, axis=0, return_counts=True)  # fasta.py:547
+    msa = [SimpleNamespace(description=nm, seq=s) for nm, s in zip(names, seqs)]
+    tip, S = ref.fasta._process_tips(msa, {nm: i for i, nm in enumerate(names)}, {nm: nm for nm in names})  # fasta.py:539-548
+    pat, cnt = tip.partials, tip.counts
     codes = (pat.astype(np.uint8) << np.arange(4, dtype=np.uint8)).sum(-1)
-    json.dump({"source": "example/hcv.nexus", "names": names, "seqs": seqs, "n_patterns": int(len(pat)),
-               "counts": cnt.tolist(), "first_column_codes": codes[:, 0].tolist()},
+    json.dump({"source": "example/hcv.nexus", "generated_by": GENERATED_BY, "names": names, "seqs": seqs,
+               "n_patterns": int(S), "counts": cnt.tolist(), "first_column_codes": codes[:, 0].tolist()},
               open(os.path.join(HERE, "hcv_patterns.json"), "w"))
     return names, seqs
 
@@ -48,6 +76,21 @@ def ladder_newick(names, times):
     return s + ";"
 
 
+def _ref_tree(newick):
+    with ref.active():
+        rtd, nm = ref.tree_data.TreeData.from_newick(newick)
+    o, onm = otd.TreeData.from_newick(newick)
+    assert nm == onm
+    for f in ("postorder", "child_parent", "parent_child", "sample_times"):
+        assert np.array_equal(np.asarray(getattr(rtd, f)), getattr(o, f)), f
+    return rtd, o, nm
+
+
+def _tree_json(rtd):
+    return {"postorder": np.asarray(rtd.postorder).tolist(), "child_parent": np.asarray(rtd.child_parent).tolist(),
+            "parent_child": np.asarray(rtd.parent_child).tolist(), "sample_times": np.asarray(rtd.sample_times, dtype=float).tolist()}
+
+
 def sims(kind="constant", ntaxa=12, nsites=300):
     xml = open(os.path.join(REF, "paper", "sims", kind, "xmls", "sim1.xml")).read()
     rows = re.findall(r'<sequence[^>]*taxon="([^"]+)"[^>]*value="([^"]+)"', xml)
@@ -58,45 +101,248 @@ def sims(kind="constant", ntaxa=12, nsites=300):
     dates = np.array([float(nm.split("_")[1]) for nm in names])
     times = dates.max() - dates
     newick = ladder_newick(names, times)
-    td, nm = otd.TreeData.from_newick(newick)
-    tip, S = otips.process_tips(names, seqs, nm)
-    Q = osub.JC69()
+    rtd, o, nm = _ref_tree(newick)
+    msa = [SimpleNamespace(description=n_, seq=s) for n_, s in zip(names, seqs)]
+    tip, S = ref.fasta._process_tips(msa, nm, {n_: n_ for n_ in names})
+    otip, oS = otips.process_tips(names, seqs, nm)
+    assert S == oS and np.array_equal(tip.partials, otip.partials)
+    Qr, Qo = ref.substitution.JC69(), osub.JC69()
     rng = np.random.default_rng(11)
-    n = td.n
-    import torch
-
-    torch.set_default_dtype(torch.float64)
-    m = 5
-    params = dict(
-        proportions=torch.tensor(rng.uniform(0.2, 0.8, n - 2)), root_proportion=torch.tensor([0.55]),
-        origin=torch.tensor([2.5]), origin_start=torch.tensor([float(td.sample_times.max())]),
-        R=torch.tensor(rng.lognormal(0.3, 0.3, m)), delta=torch.full((m,), 1.5, dtype=torch.float64),
-        s=torch.full((m,), 0.3, dtype=torch.float64), rho=torch.zeros(m, dtype=torch.float64),
-        clock_rate=torch.tensor([0.02], dtype=torch.float64))
-    for v in params.values():
-        v.requires_grad_(True)
-    ll, parts = obdsky.loglik(params, td, tip, Q, return_parts=True)
-    ll.backward()
-    bl = (parts["branch_lengths"] * params["clock_rate"][0]).detach().numpy()
-    site_ll = oprune.prune_loglik(bl, Q, tip.partials, td)
-    _, gbl = oprune.prune_loglik_and_grad(bl, Q, tip.partials, td)
+    n, m = rtd.n, 5
+    params = dict(proportions=rng.uniform(0.2, 0.8, n - 2), root_proportion=np.array([0.55]), origin=np.array([2.5]),
+                  origin_start=np.array([float(np.asarray(rtd.sample_times).max())]), R=rng.lognormal(0.3, 0.3, m),
+                  delta=np.full(m, 1.5), s=np.full(m, 0.3), rho=np.zeros(m), clock_rate=np.array([0.02]))
+    rtip = ref.util.TipData(tip.partials, tip.counts)
+    c = (True, True, True)
+    ll, grads = jax.value_and_grad(lambda p: ref.bdsky.loglik(p, rtd, rtip, Qr, c))({k: jnp.array(v) for k, v in params.items()})
+    tree_ll = ref.bdsky.loglik({k: jnp.array(v) for k, v in params.items()}, rtd, rtip, Qr, (False, True, False))
+    data_ll = ref.bdsky.loglik({k: jnp.array(v) for k, v in params.items()}, rtd, rtip, Qr, (False, False, True))
+    # intermediate quantities, computed with the reference's statements (bdsky.py:298-307)
+    root_height = params["root_proportion"][0] * (params["origin"][0] + params["origin_start"][0] - np.asarray(rtd.sample_times).max())
+    node_heights = rtd.height_transform(root_height, jnp.array(params["proportions"]))
+    bl = np.asarray(node_heights[rtd.child_parent[:-1]] - node_heights[:-1]) * params["clock_rate"][0]
+    vm = jax.vmap(ref.prune.prune_loglik, (None, None, 0, None, None, None))
+    site_ll = np.asarray(vm(jnp.array(bl), Qr, tip.partials, rtd, True, False))
+    _, gbl = jax.value_and_grad(lambda b: (vm(b, Qr, tip.partials, rtd, True, False) * tip.counts).sum())(jnp.array(bl))
+    # the oracle must agree before the fixture is written
+    op = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+    oll, parts = obdsky.loglik(op, o, TipData(otip.partials, otip.counts), Qo, return_parts=True)
+    oll.backward()
+    _close(oll.item(), float(ll), what="loglik")
+    _close(parts["tree"].item(), float(tree_ll), what="tree")
+    _close(parts["data"].item(), float(data_ll), what="data")
+    for k in params:
+        if op[k].grad is not None:
+            _close(op[k].grad.numpy(), np.asarray(grads[k]), 1e-10, what=k)
+    _close(oprune.prune_loglik(bl, Qo, otip.partials, o), site_ll, what="site_ll")
     out = {
-        "source": f"paper/sims/{kind}/xmls/sim1.xml (first {ntaxa} taxa, first {nsites} sites)", "newick": newick,
-        "names": names, "seqs": seqs, "model": "JC69",
-        "tree": {"postorder": td.postorder.tolist(), "child_parent": td.child_parent.tolist(),
-                 "parent_child": td.parent_child.tolist(), "sample_times": td.sample_times.tolist()},
-        "n_patterns": int(S), "counts": tip.counts.tolist(),
-        "params": {k: v.detach().numpy().tolist() for k, v in params.items()},
-        "grads": {k: v.grad.numpy().tolist() for k, v in params.items() if v.grad is not None},
-        "loglik": ll.item(), "tree_loglik": parts["tree"].item(), "data_loglik": parts["data"].item(),
-        "node_heights": parts["node_heights"].detach().numpy().tolist(), "branch_lengths_scaled": bl.tolist(),
-        "site_ll": site_ll.tolist(), "dll_dbl": (gbl * tip.counts[:, None]).sum(0).tolist(),
+        "source": f"paper/sims/{kind}/xmls/sim1.xml (first {ntaxa} taxa, first {nsites} sites)", "generated_by": GENERATED_BY,
+        "newick": newick, "names": names, "seqs": seqs, "model": "JC69", "tree": _tree_json(rtd),
+        "n_patterns": int(S), "counts": tip.counts.tolist(), "params": {k: v.tolist() for k, v in params.items()},
+        "grads": {k: np.asarray(v).tolist() for k, v in grads.items()},
+        "loglik": float(ll), "tree_loglik": float(tree_ll), "data_loglik": float(data_ll),
+        "node_heights": np.asarray(node_heights).tolist(), "branch_lengths_scaled": bl.tolist(),
+        "site_ll": site_ll.tolist(), "dll_dbl": np.asarray(gbl).tolist(),
     }
     json.dump(out, open(os.path.join(HERE, f"sims_{kind}_sim1.json"), "w"))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 1: the HCV example as example/example.ipynb sets it up (flows, prior, clock rate, M = 10, Adagrad)
+# ---------------------------------------------------------------------------------------------------------------------
+M_INTERVALS = 10
+CLOCK = 0.79e-3
+
+
+def example_flows(n_tips_per_tree):
+    """example.ipynb cells 5-6: global and local flows of the HCV walkthrough."""
+    F, Tr, Const = ref.fasta, ref.prob_transform.Transform, ref.prob_distribution.Constant
+    m = M_INTERVALS
+    gf = ref.prob.VF(origin=Tr(1, F.pos), origin_start=Const(0.0), delta=Tr(m, F.pos), R=Tr(m, F.pos), rho_m=Tr(1, F.z1),
+                     s=Const(np.repeat(0.00, m)), precision_R=Tr(1, F.pos), precision_delta=Tr(1, F.pos),
+                     clock_rate=Const(CLOCK))
+    lfs = [{"proportions": Tr(n - 2, F.z1), "root_proportion": Tr(1, F.z1)} for n in n_tips_per_tree]
+    return gf, lfs
+
+
+def example_prior(params):
+    """example.ipynb cell 7, verbatim semantics."""
+    xlogy = jax.scipy.special.xlogy
+    ll = 0
+    tau = {"R": params["precision_R"][0], "delta": params["precision_delta"][0]}
+    ll += jax.scipy.stats.gamma.logpdf(tau["R"], a=0.001, scale=1 / 0.001)
+    ll += jax.scipy.stats.gamma.logpdf(tau["delta"], a=0.001, scale=1 / 0.001)
+    ll += jax.scipy.stats.beta.logpdf(params["rho_m"], 1, 9999).sum()
+    mus = [1.0, 1.0, 1.0]
+    sigmas = [1.25, 1.25, 1.25]
+    for i, k in enumerate(["R", "delta", "origin"]):
+        log_rate = jnp.log(params[k])
+        ll += ref.bdsky._lognorm_logpdf(log_rate, mu=mus[i], sigma=sigmas[i]).sum()
+    for k in ["R", "delta"]:
+        log_rate = jnp.log(params[k])
+        ll -= (tau[k] / 2) * (jnp.diff(log_rate) ** 2).sum()
+        m = len(log_rate)
+        ll += xlogy((m - 1) / 2, tau[k] / (2 * jnp.pi))
+    return ll
+
+
+def oracle_example_prior(p):
+    """The same prior on torch tensors (for the oracle-side assertion)."""
+    ln = lambda lx, mu_, sig: (math.log(2 * math.pi) + ((lx - mu_) / sig) ** 2) / -2 - lx - math.log(sig)
+    gam = lambda x, a, scale: (a - 1) * torch.log(x / scale) - x / scale - math.lgamma(a) - math.log(scale)
+    tau = {"R": p["precision_R"][0], "delta": p["precision_delta"][0]}
+    ll = gam(tau["R"], 0.001, 1 / 0.001) + gam(tau["delta"], 0.001, 1 / 0.001)
+    a, b = 1.0, 9999.0
+    x = p["rho_m"]
+    ll = ll + ((a - 1) * torch.log(x) + (b - 1) * torch.log1p(-x) - (math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b))).sum()
+    for k in ("R", "delta", "origin"):
+        ll = ll + ln(torch.log(p[k]), 1.0, 1.25).sum()
+    for k in ("R", "delta"):
+        lr = torch.log(p[k])
+        ll = ll - (tau[k] / 2) * (torch.diff(lr) ** 2).sum()
+        ll = ll + (len(lr) - 1) / 2 * torch.log(tau[k] / (2 * math.pi))
+    return ll
+
+
+GLOBAL_KINDS = {"origin": "pos", "delta": "pos", "R": "pos", "rho_m": "z1", "precision_R": "pos", "precision_delta": "pos"}
+
+
+def _oracle_flows(flows):
+    Const = ref.prob_distribution.Constant
+    out = {}
+    for k, v in flows.items():
+        if isinstance(v, Const):
+            out[k] = ("const", np.atleast_1d(v.c).astype(float).tolist())
+        else:
+            out[k] = (GLOBAL_KINDS.get(k, "z1"), int(v.dim))
+    return out
+
+
+def _t1(p):
+    return p["transform"]["t1"]
+
+
+def config1(names, seqs, n_trees=3, n_tips=10, n_iter=2, seed=0):
+    rng = np.random.default_rng(seed)
+    tds, otds, tip_r, tip_o, rows_all, newicks = [], [], [], [], [], []
+    for t in range(n_trees):
+        rows = rng.choice(len(names), n_tips, replace=False)  # fasta.py:253
+        sub_names, sub_seqs = [names[i] for i in rows], [seqs[i].upper() for i in rows]
+        D = otb.snp_dists(sub_seqs)
+        r, c = np.tril_indices(n_tips, -1)
+        mat, _ = otb.get_distance_matrix(D[(r, c)].astype(float), np.zeros(n_tips), single_theta=False)
+        _, _, nested = otb.upgma(mat, sub_names)
+        newick = otb.nested_to_newick(nested)
+        rtd, o, nm = _ref_tree(newick)
+        rtd.sample_times[:] = 0.0  # fasta.py:529-537 (_process_tree): contemporaneous sample, dates = 1993.0
+        o.sample_times[:] = 0.0
+        msa = [SimpleNamespace(description=n_, seq=s) for n_, s in zip(sub_names, sub_seqs)]
+        tr, _ = ref.fasta._process_tips(msa, nm, {n_: n_ for n_ in sub_names})
+        to, _ = otips.process_tips(sub_names, sub_seqs, nm)
+        tds.append(rtd), otds.append(o), tip_r.append(tr), tip_o.append(to), rows_all.append(rows.tolist()), newicks.append(newick)
+    holder = SimpleNamespace(tip_data_cs=list(tip_r), max_partial_count=max(t.partials.shape[0] for t in tip_r))
+    ref.fasta.SeqData.pad_tips(holder)  # fasta.py:325-331
+    tip_r = holder.tip_data_cs
+    tip_o = otips.pad_tips(tip_o)
+    for a, b in zip(tip_r, tip_o):
+        assert np.array_equal(a.partials, b.partials) and np.array_equal(a.counts, b.counts)
+
+    gf, lfs = example_flows([n_tips] * n_trees)
+    Qr, Qo = ref.substitution.HKY(2.7), osub.HKY(2.7)
+    c = ((True, True), (True, True, True))
+
+    # --- (1) one `step` per tree at fixed parameters: the M = 10 single-sample value_and_grad(loss) calls of
+    #     fasta.py:403-427, values and gradients, with the base draws recorded
+    prm_rng = np.random.default_rng(seed + 1)
+    gparams = jax.tree_util.tree_map(lambda x: prm_rng.normal(size=np.shape(x)) * 0.1, {k: v.params for k, v in gf.items()})
+    lparams = [jax.tree_util.tree_map(lambda x: prm_rng.normal(size=np.shape(x)) * 0.1, {k: v.params for k, v in lf.items()})
+               for lf in lfs]
+    M = 10
+    steps = []
+    for j in range(n_trees):
+        flows = ref.prob.VF(gf | lfs[j])
+        p = gparams | lparams[j]
+        names_tr = [k for k, v in flows.items() if not isinstance(v, ref.prob_distribution.Constant)]
+        key = jax.random.PRNGKey(100 + j)
+        fvals, eps_all = [], []
+        gsum = None
+        for k_ in range(M):
+            key, sub = jax.random.split(key)
+            rec = []
+            ref.core.random.recorder = rec
+            f, g = ref.fasta._loss(p, flows, tds[j], tip_r[j], sub, Qr, c, False, True, example_prior)  # fasta.py:409
+            ref.core.random.recorder = None
+            eps = {nm_: r_[1].reshape(-1) for nm_, r_ in zip(names_tr, rec)}
+            # oracle agreement for this sample
+            op = {nm_: {kk: torch.tensor(np.asarray(_t1(p[nm_])[kk]), requires_grad=True) for kk in ("mu", "log_sigma")} for nm_ in names_tr}
+            fo = oopt.loss(op, _oracle_flows(flows), otds[j], tip_o[j], eps, Qo, c, True, oracle_example_prior)
+            # short branches (clock 7.9e-4): the reference's P @ (exp(t d) * (Pinv @ p)) carries ~1e-16/t relative rounding
+            # noise per site, so two correct evaluations with different summation order agree to ~1e-11 here, not 1e-13
+            _close(fo.item(), float(f), 1e-10, what="loss")
+            fo.backward()
+            for nm_ in names_tr:
+                for kk in ("mu", "log_sigma"):
+                    _close(op[nm_][kk].grad.numpy(), np.asarray(_t1(g[nm_])[kk]), 1e-8, what=(nm_, kk))
+            fvals.append(float(f))
+            eps_all.append({nm_: e.tolist() for nm_, e in eps.items()})
+            g = jax.tree_util.tree_map(jnp.nan_to_num, g)
+            gsum = g if gsum is None else jax.tree_util.tree_map(jnp.add, gsum, g)
+        gmean = jax.tree_util.tree_map(lambda x: x / M, gsum)
+        steps.append({"eps": eps_all, "loss_per_sample": fvals, "loss": float(np.mean(np.nan_to_num(fvals))),
+                      "grad": {nm_: {kk: np.asarray(_t1(gmean[nm_])[kk]).tolist() for kk in ("mu", "log_sigma")} for nm_ in names_tr}})
+        print(f"config1 step tree {j}: loss {steps[-1]['loss']:.6f}")
+
+    # --- (2) the reference's own SeqData.loop (fasta.py:387-522) for n_iter iterations
+    sd = ref.fasta.SeqData.__new__(ref.fasta.SeqData)
+    sd.tds, sd.tip_data_cs = tds, tip_r
+    sd.setup_flows(gf, lfs)
+    np.random.seed(seed + 2)  # loop() initialises the variational parameters with np.random.normal (fasta.py:439-446)
+    state = np.random.get_state()
+    init_g = jax.tree_util.tree_map(lambda x: np.random.normal(size=np.shape(x)) * 0.1, {k: v.params for k, v in gf.items()})
+    init_l = [jax.tree_util.tree_map(lambda x: np.random.normal(size=np.shape(x)) * 0.1, {k: v.params for k, v in lf.items()})
+              for lf in lfs]
+    np.random.set_state(state)
+    rec = []
+    ref.core.random.recorder = rec
+    # (loop() ends with 10,000 posterior draws per flow, fasta.py:494-522: slow under the shim, irrelevant here)
+    res = sd.loop(example_prior, jax.random.PRNGKey(6), n_iter=n_iter, step_size=1.0, Q=Qr, threshold=0.0)
+    ref.core.random.recorder = None
+    fs = [[float(x) for x in row] for row in res.fs]
+    print("config1 loop fs:", fs)
+    # draws of the fitting phase only: n_iter * n_trees * M * (#Transform flows) of shape (1, dim)
+    n_tr = len([k for k, v in (gf | lfs[0]).items() if not isinstance(v, ref.prob_distribution.Constant)])
+    fit_draws = rec[: n_iter * n_trees * M * n_tr]
+    assert all(r_[1].shape[0] == 1 for r_ in fit_draws)
+    names_tr = [k for k, v in (gf | lfs[0]).items() if not isinstance(v, ref.prob_distribution.Constant)]
+    loop_eps, pos = [], 0
+    for i in range(n_iter):
+        row = []
+        for j in range(n_trees):
+            samples = []
+            for k_ in range(M):
+                samples.append({nm_: fit_draws[pos + q][1].reshape(-1).tolist() for q, nm_ in enumerate(names_tr)})
+                pos += n_tr
+            row.append(samples)
+        loop_eps.append(row)
+
+    flat = lambda tree: {nm_: {kk: np.asarray(_t1(tree[nm_])[kk]).tolist() for kk in ("mu", "log_sigma")} for nm_ in tree
+                         if "transform" in tree[nm_] and "t1" in tree[nm_]["transform"]}
+    out = {
+        "source": "example/hcv.nexus set up as example/example.ipynb (flows, prior, clock rate, HKY(2.7), M = 10, adagrad(1.0))",
+        "generated_by": GENERATED_BY, "n_trees": n_trees, "n_tips": n_tips, "m": M_INTERVALS, "clock_rate": CLOCK, "kappa": 2.7,
+        "rows": rows_all, "newicks": newicks, "trees": [_tree_json(t) for t in tds],
+        "n_patterns_padded": int(tip_r[0].partials.shape[0]), "counts": [t.counts.tolist() for t in tip_r],
+        "flows": _oracle_flows(gf | lfs[0]),
+        "step": {"global_params": flat(gparams), "local_params": [flat(lp) for lp in lparams], "per_tree": steps},
+        "loop": {"n_iter": n_iter, "step_size": 1.0, "init_global": flat(init_g), "init_local": [flat(lp) for lp in init_l],
+                 "eps": loop_eps, "fs": fs},
+    }
+    json.dump(out, open(os.path.join(HERE, "config1_hcv_example.json"), "w"))
+
+
 if __name__ == "__main__":
-    hcv()
+    names, seqs = hcv()
     for kind in ("constant", "zigzag"):
         sims(kind)
+    config1(names, seqs)
     print("golden fixtures written to", HERE)
