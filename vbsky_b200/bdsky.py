@@ -65,7 +65,7 @@ def tree_loglik(lam, psi, mu, rho, xs, times, n: int, condition_on_survival: boo
 
 class _Loglik(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ens, unit_tree, m, flags, want_parts, *vals):
+    def forward(ctx, ens, unit_tree, m, flags, clean, *vals):
         params = dict(zip(PARAM_KEYS, vals))
         U = params["root_proportion"].shape[0]
         dev = ens.device
@@ -97,6 +97,9 @@ class _Loglik(torch.autograd.Function):
             _lib.check(_lib.lib.vbsky_loglik_value_and_grad(
                 ens._layout, ens._tips, U, _p(unit_tree), m, C.byref(cin), C.byref(ens._model), flags,
                 _p(ll), _p(lt), _p(ld), None if cg is None else C.byref(cg), _p(ws), ws.numel(), _stream(dev)))
+        if clean:  # fasta.py:421: nan_to_num on every single-sample (value, gradient) before they are averaged
+            ll = torch.nan_to_num(ll)
+            grads = {k: (None if v is None else torch.nan_to_num(v)) for k, v in grads.items()}
         ctx.grads = grads
         ctx.mark_non_differentiable(lt, ld)
         return ll, lt, ld
@@ -116,12 +119,14 @@ class _Loglik(torch.autograd.Function):
 
 
 def loglik(params: Dict[str, torch.Tensor], ens, unit_tree: torch.Tensor, c=(True, True, True),
-           condition_on_survival: bool = True, params_prior_loglik=None, return_parts: bool = False):
+           condition_on_survival: bool = True, params_prior_loglik=None, return_parts: bool = False, clean: bool = False):
     """bdsky.loglik for U units.  ``params`` holds CUDA fp64 tensors with a leading unit axis:
     proportions [U, n-2], root_proportion/origin/origin_start/clock_rate [U] (or [U, 1]), R/delta/s/rho
     [U, m]; ``ens`` is the device-resident ``Ensemble``; ``unit_tree`` [U] int32 picks each unit's tree.
     ``c = (prior, tree, data)`` switches the three terms as in the reference (bdsky.py:288,323,331);
     the prior term is the user's ``params_prior_loglik(params)`` -> [U] evaluated in torch.
+    ``clean=True`` applies ``nan_to_num`` to every unit's value and gradient rows, which is what the reference's ``step``
+    does to each single-sample (f, g) before averaging (fasta.py:421), so one non-finite draw is dropped, not spread.
     Only equidistant skyline intervals (the reference's default, bdsky.py:314) are supported here."""
     U = unit_tree.shape[0]
     n = ens.n
@@ -139,7 +144,7 @@ def loglik(params: Dict[str, torch.Tensor], ens, unit_tree: torch.Tensor, c=(Tru
     if c[1]:
         assert flat["R"].shape == flat["s"].shape == flat["delta"].shape == flat["rho"].shape  # bdsky.py:283
     flags = (TERM_TREE if c[1] else 0) | (TERM_DATA if c[2] else 0) | (CONDITION_ON_SURVIVAL if condition_on_survival else 0)
-    ll, lt, ld = _Loglik.apply(ens, unit_tree, m, flags, return_parts, *[flat[k] for k in PARAM_KEYS])
+    ll, lt, ld = _Loglik.apply(ens, unit_tree, m, flags, bool(clean), *[flat[k] for k in PARAM_KEYS])
     if c[0] and params_prior_loglik is not None:
         ll = ll + params_prior_loglik(params)
     if return_parts:

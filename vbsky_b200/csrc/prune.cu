@@ -33,6 +33,8 @@
 //     staging buffer, written as per-tile partials and summed in a fixed order by finalize_kernel
 //     (bitwise reproducible).
 #include <cmath>
+#include <map>
+#include <utility>
 #include <type_traits>
 
 #include "common.h"
