@@ -285,6 +285,20 @@ int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips,
                                 double* ll_tree, double* ll_data, vbsky_param_grads* grads,
                                 void* ws, size_t ws_bytes, void* stream);
 
+/* The reduction step of one ensemble ELBO evaluation (no counterpart in the reference, which visits
+ * trees one at a time, fasta.py:456-487): from the per-unit outputs of vbsky_loglik_value_and_grad build the payload
+ * of the single all-reduce,
+ *   out[0]                      = scale * sum_u ll[u]
+ *   out[1], out[2]              = scale * sum_u d/d origin, d/d clock_rate
+ *   out[3 + i*m + j]            = scale * sum_u d/d {R, delta, s, rho}[u][j]                  (i = 0..3; NULL => 0)
+ *   out[3 + 4m + t*(n-1) + j]   = scale * sum_{u of tree t} d/d proportions[u][j] (j < n-2), d/d root_proportion[u] (j = n-2)
+ * (scale = 1/K for the mean over Monte-Carlo draws, optim.py:74).  unit_tree [U] must be non-decreasing (units
+ * grouped by tree).  Fixed summation order.  vbsky_reduce_elbo_count = 3 + 4m + T(n-1) doubles.             */
+int64_t vbsky_reduce_elbo_count(int32_t T, int32_t n, int32_t m);
+int vbsky_reduce_elbo(int32_t U, int32_t T, int32_t n, int32_t m, const int32_t* unit_tree,
+                      const double* ll, const vbsky_param_grads* grads, double scale, double* out,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Local variational family (the per-tree flows of fasta.py:378-384): reparameterised samples
  *   x = clip(expit(mu + exp(log_sigma) * eps), 1e-7, 1-1e-7)

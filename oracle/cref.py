@@ -21,6 +21,13 @@ def _load():
 _lib = None
 
 
+def set_threads(n: int) -> None:
+    """Explicit OpenMP thread count (launchers such as torchrun export OMP_NUM_THREADS=1)."""
+    global _lib
+    _lib = _lib or _load()
+    _lib.vbsky_oracle_set_threads(int(n))
+
+
 def threads() -> int:
     global _lib
     _lib = _lib or _load()

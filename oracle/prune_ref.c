@@ -52,6 +52,10 @@ static inline void expm_action(const double* P, const double* Pinv, const double
   }
 }
 
+void vbsky_oracle_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
 int vbsky_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -150,9 +150,13 @@ class EnsembleELBO:
         return eps
 
     # ------------------------------------------------------------------------------------------------------------
-    def elbo(self, trees: Optional[Sequence[int]] = None, eps: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    def elbo(self, trees: Optional[Sequence[int]] = None, eps: Optional[Dict[str, torch.Tensor]] = None,
+             shard: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """ELBO of the whole ensemble, or of the given trees only (``-loss`` of optim.py:35-78 for one tree).
-        ``eps``: base draws {flow: [K, dim], "local": [U, n-1]} (units tree-major, K contiguous); drawn if omitted."""
+        ``eps``: base draws {flow: [K, dim], "local": [U, n-1]} (units tree-major, K contiguous); drawn if omitted.
+        ``shard=(rank, world)``: this rank's share -- the likelihood and local-entropy terms of units u with
+        u % world == rank plus 1/world of the global entropy and prior terms -- so that the sum over ranks is the ELBO
+        and the sum of ``theta.grad`` over ranks its gradient (every rank must use the same ``eps``)."""
         ens, K, m = self.ens, self.K, self.m
         n, dev = ens.n, ens.device
         par = self.params
@@ -167,6 +171,7 @@ class EnsembleELBO:
         U = T * K
         if eps is None:
             eps = self.sample_eps(T)
+        rank, world = (0, 1) if shard is None else shard
         samples: Dict[str, torch.Tensor] = {}
         val = torch.zeros((), dtype=torch.float64, device=dev)
         for name, (kind, _) in self.flows.items():
@@ -180,9 +185,14 @@ class EnsembleELBO:
         # local family: one row of (mu, log_sigma) per unit; expand's backward is a fixed-order sum over the K draws
         d = n - 1
         e_l = torch.as_tensor(eps["local"], dtype=torch.float64, device=dev).reshape(U, d)
-        x, lq_local = local_flow_rows(mu_l.unsqueeze(1).expand(T, K, d).reshape(U, d),
-                                      ls_l.unsqueeze(1).expand(T, K, d).reshape(U, d), e_l)
+        mu_u, ls_u = mu_l.unsqueeze(1).expand(T, K, d).reshape(U, d), ls_l.unsqueeze(1).expand(T, K, d).reshape(U, d)
         per_unit = lambda v: v.unsqueeze(0).expand(T, K, v.shape[-1]).reshape(U, v.shape[-1])
+        if world > 1:
+            mine = torch.arange(rank, U, world, device=dev)  # ascending: unit_tree stays grouped by tree
+            mu_u, ls_u, e_l, unit_tree = mu_u[mine], ls_u[mine], e_l[mine], unit_tree[mine]
+            full = per_unit
+            per_unit = lambda v: full(v)[mine]
+        x, lq_local = local_flow_rows(mu_u, ls_u, e_l)
         p = {
             "proportions": x[:, : n - 2], "root_proportion": x[:, n - 2],
             "origin": per_unit(samples["origin"])[:, 0], "origin_start": per_unit(samples["origin_start"])[:, 0],
@@ -190,10 +200,11 @@ class EnsembleELBO:
             "delta": per_unit(samples["delta"]), "s": per_unit(samples["s"]), "rho": per_unit(samples["rho"]),
         }
         ll = bdsky.loglik(p, ens, unit_tree, c=(False, True, True), clean=True)
-        val = val + ll.view(T, K).sum(0).mean() - lq_local.view(T, K).mean(1).sum()
         if self.prior_fn is not None:
             val = val + self.prior_fn(samples).mean()
-        return val
+        if world > 1:
+            return val / world + (ll.sum() - lq_local.sum()) / K
+        return val + ll.view(T, K).sum(0).mean() - lq_local.view(T, K).mean(1).sum()
 
     # ------------------------------------------------------------------------------------------------------------
     def fit(self, n_iter: int = 10, step_size: float = 1.0, callback=None, sequential: bool = False, eps_fn=None):
@@ -207,12 +218,23 @@ class EnsembleELBO:
         with separate optimiser states (fasta.py:448-449, 456-483); returns losses [n_iter][T].
         ``eps_fn(i, j) -> eps`` (j = None in batched mode) injects the base draws of a visit."""
         if not sequential:
+            import torch.distributed as dist
+
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            shard = (dist.get_rank(), world) if world > 1 else None
             opt = Adagrad(self.theta.data, step_size=step_size)
             hist = []
             for i in range(n_iter):
                 self.theta.grad = None
-                loss = -self.elbo(eps=None if eps_fn is None else eps_fn(i, None))
+                # multi-GPU: every rank draws the same eps (same seed), evaluates its units and the gradient of the
+                # whole parameter block -- global AND per-tree -- is summed over ranks, so all replicas stay identical
+                loss = -self.elbo(eps=None if eps_fn is None else eps_fn(i, None), shard=shard)
                 loss.backward()
+                if world > 1:
+                    red = torch.cat([self.theta.grad, loss.detach().reshape(1)])
+                    dist.all_reduce(red)
+                    self.theta.grad.copy_(red[:-1])
+                    loss = red[-1]
                 opt.update(self.theta.grad)
                 hist.append(loss.item())
                 if callback:

@@ -1,45 +1,70 @@
-"""Multi-GPU plumbing of the ensemble ELBO: the (tree, sample) units are independent up to a final
-sum, so they are dealt round-robin to the ranks (one process per GPU) and the only exchange per
-evaluation is one small all-reduce of [ELBO value, gradient w.r.t. the global parameters]; gradients of
-per-tree (local) parameters stay on the rank that owns the unit.  torch.distributed provides the
-collective (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
-from typing import Dict, List, Sequence, Tuple
+"""Multi-GPU plumbing of the ensemble ELBO: the (tree, sample) units are independent up to a final sum, so they are
+dealt round-robin to the ranks (one process per GPU) and the only exchange per evaluation is ONE all-reduce of
+[ELBO value, gradient w.r.t. the global parameters, gradient w.r.t. every tree's local parameters].
 
-import numpy as np
+The K samples of one tree land on different ranks (that is what balances 1000 units over 8 GPUs), so every rank holds
+only a partial sum of a tree's local gradient: the local block is therefore part of the all-reduce payload
+(3 + 4m + T(n-1) doubles; 160 KB at 100 trees x 200 tips -- latency-bound over NVLink), after which every rank holds
+the complete gradient and applies the same optimiser update.  The payload is built by one kernel
+(``vbsky_reduce_elbo``, fixed summation order).  torch.distributed provides the collective (NCCL over NVLink on GPUs;
+gloo in the CPU tests of the host logic)."""
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 GLOBAL_KEYS = ("origin", "clock_rate", "R", "delta", "s", "rho")
 
 
 def shard_units(T: int, K: int, rank: int, world: int) -> List[Tuple[int, int]]:
     """Units (tree t, sample k) owned by ``rank``: unit index u = t*K + k, taken round-robin (u % world == rank)
-    so that T*K = 1000 units split 125/125/... over 8 ranks instead of 13/12 trees."""
+    so that T*K = 1000 units split 125/125/... over 8 ranks instead of 13/12 trees.  The returned list is ordered by
+    unit index, i.e. grouped by tree (what ``reduce_elbo`` requires)."""
     return [(u // K, u % K) for u in range(rank, T * K, world)]
 
 
-def pack_global(ll: torch.Tensor, grads: Dict[str, torch.Tensor], K: int, out: torch.Tensor = None) -> torch.Tensor:
-    """[sum_u ll_u / K, sum_u d/d(global param) / K ...] as one flat fp64 vector (the all-reduce payload)."""
-    parts = [ll.sum().reshape(1)]
-    for k in GLOBAL_KEYS:
-        g = grads[k]
-        parts.append(g.sum(0).reshape(-1) if g.dim() > 1 else g.sum().reshape(1))
-    v = torch.cat(parts) / K
-    if out is not None:
-        out.copy_(v)
-        return out
-    return v
+def payload_count(T: int, n: int, m: int) -> int:
+    return 3 + 4 * m + T * (n - 1)
+
+
+def reduce_elbo(unit_tree: torch.Tensor, ll: torch.Tensor, grads: Dict[str, torch.Tensor], T: int, n: int, m: int, K: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``vbsky_reduce_elbo``: per-unit ll [U] and gradients (``Ensemble.GRAD_KEYS`` -> [U, ...]) of this rank's units ->
+    the all-reduce payload [sum ll / K, sum d/d(origin, clock_rate, R, delta, s, rho) / K, per-tree sum of
+    d/d(proportions, root_proportion) / K].  ``unit_tree`` (int32 [U]) must be non-decreasing."""
+    dev = ll.device
+    if out is None:
+        out = torch.empty(payload_count(T, n, m), dtype=torch.float64, device=dev)
+    cg = _lib.ParamGrads()
+    keep = []
+    for k in ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho"):
+        v = grads.get(k)
+        if v is not None and v.numel():
+            v = v.contiguous()
+            keep.append(v)
+            setattr(cg, k, v.data_ptr())
+        else:
+            setattr(cg, k, 0)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.lib.vbsky_reduce_elbo(ll.shape[0], T, n, m, C.c_void_p(unit_tree.data_ptr()), C.c_void_p(ll.data_ptr()),
+                                              C.byref(cg), 1.0 / K, C.c_void_p(out.data_ptr()), st))
+    return out
 
 
 def allreduce_elbo(vec: torch.Tensor, group=None) -> torch.Tensor:
-    """Sum the packed vector over ranks in place (no-op without an initialised process group)."""
+    """Sum the payload over ranks in place (no-op without an initialised process group)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
     return vec
 
 
-def unpack_global(vec: torch.Tensor, m: int) -> Dict[str, torch.Tensor]:
+def unpack_payload(vec: torch.Tensor, T: int, n: int, m: int) -> Dict[str, torch.Tensor]:
     out = {"elbo": vec[0], "origin": vec[1], "clock_rate": vec[2]}
     for i, k in enumerate(("R", "delta", "s", "rho")):
         out[k] = vec[3 + i * m: 3 + (i + 1) * m]
+    out["local"] = vec[3 + 4 * m:].view(T, n - 1)  # [:, :n-2] proportions, [:, n-2] root_proportion
     return out

@@ -2,18 +2,32 @@
 coalescent-shaped trees numbered like ``TreeData.from_nx``, heterochronous sampling times,
 sequences evolved down each tree under the substitution model plus a fraction of missing data.
 Used by bench.py and the tests; not part of the likelihood path."""
-from typing import List, NamedTuple, Optional
+from typing import Any, List, NamedTuple, Optional
 
 import numpy as np
 
-from .substitution import SubstitutionModel
-from .tips import PackedTips, compress_patterns
-from .tree_data import TreeData
+# NumPy only at module level: bench.py's reference arm loads this file by path (without importing the package, so that
+# the product's shared library is never mapped into the reference process) and passes the oracle's tree class.
+# The package-relative imports below happen lazily, only when the product's classes are wanted.
+SubstitutionModel = Any
+TreeData = Any
 
 
-def random_tree(n: int, rng: np.random.Generator, caterpillar: bool = False) -> TreeData:
+class _Tips(NamedTuple):
+    patterns: np.ndarray  # uint8 [S, n] state masks
+    counts: np.ndarray    # float64 [S]
+
+
+def _product_tree_from_edges(edges):
+    from .tree_data import TreeData as PTD
+
+    return PTD.from_edges(edges)[0]
+
+
+def random_tree(n: int, rng: np.random.Generator, caterpillar: bool = False, tree_from_edges=None) -> TreeData:
     """Random binary topology: repeatedly join two uniformly chosen live lineages (Kingman shape),
-    or a ladder if ``caterpillar``; sample_times ~ U(0,1) with the most recent tip at 0."""
+    or a ladder if ``caterpillar``; sample_times ~ U(0,1) with the most recent tip at 0.
+    ``tree_from_edges(edges) -> TreeData``-like (default: the product's ``TreeData.from_edges``)."""
     live = [("t", i) for i in range(n)]
     kids = {}
     k = 0
@@ -37,10 +51,10 @@ def random_tree(n: int, rng: np.random.Generator, caterpillar: bool = False) -> 
             for v in kids[u]:
                 edges.append((u, v))
             stack.extend(reversed(kids[u]))
-    td, _ = TreeData.from_edges(edges)
+    td = (tree_from_edges or _product_tree_from_edges)(edges)
     st = rng.uniform(0.0, 1.0, n)
     st[rng.integers(n)] = 0.0
-    return TreeData(td.postorder, td.child_parent, td.parent_child, st)
+    return type(td)(td.postorder, td.child_parent, td.parent_child, st)
 
 
 class SampledHeights(NamedTuple):
@@ -108,7 +122,7 @@ def evolve_codes_cuda(td: TreeData, bl: np.ndarray, Q: SubstitutionModel, L: int
 
 class SyntheticEnsemble(NamedTuple):
     tds: List[TreeData]
-    tips: List[PackedTips]
+    tips: List[Any]  # PackedTips-like (patterns, counts)
     heights: List[SampledHeights]
     clock_rate: float
     origin: float
@@ -116,24 +130,35 @@ class SyntheticEnsemble(NamedTuple):
 
 def make_ensemble(T: int, n: int, S: int, K: int, seed: int, Q: SubstitutionModel, clock_rate: float = 1.12e-3,
                   origin: float = 0.3, compress: bool = False, missing: float = 0.01,
-                  device=None) -> SyntheticEnsemble:
+                  device=None, tree_from_edges=None) -> SyntheticEnsemble:
     """T trees x n tips x S sites (used directly as patterns with count 1 unless ``compress``),
-    K height samples per tree.  ``device``: evolve the sequences with torch on that CUDA device."""
+    K height samples per tree.  ``device``: evolve the sequences with torch on that CUDA device (a different random
+    stream from the NumPy one; the trees and heights are the same either way)."""
     rng = np.random.default_rng(seed)
     tds, tips, hts = [], [], []
+    if tree_from_edges is None:
+        from .tips import PackedTips
+    else:
+        PackedTips = _Tips
+    # trees and heights first (one stream), sequences from a per-tree stream: the first t trees, their heights and -- on
+    # the NumPy path -- their sequences do not depend on T, so a subset of the ensemble can be regenerated on its own
     for t in range(T):
-        td = random_tree(n, rng)
-        sh = sample_heights(td, K, rng, origin)
+        td = random_tree(n, rng, tree_from_edges=tree_from_edges)
+        tds.append(td), hts.append(sample_heights(td, K, rng, origin))
+    for t in range(T):
+        td, sh = tds[t], hts[t]
         if device is not None:
             codes = evolve_codes_cuda(td, sh.branch_lengths[0] * clock_rate, Q, S, seed * 100003 + t, device, missing)
         else:
-            codes = evolve_codes(td, sh.branch_lengths[0] * clock_rate, Q, S, rng, missing)
+            codes = evolve_codes(td, sh.branch_lengths[0] * clock_rate, Q, S, np.random.default_rng([seed, t]), missing)
         if compress:
+            from .tips import compress_patterns
+
             pat, cnt = compress_patterns(codes)
             tp = PackedTips(pat, cnt.astype(np.float64))
         else:
             tp = PackedTips(codes, np.ones(S))
-        tds.append(td), tips.append(tp), hts.append(sh)
+        tips.append(tp)
     if compress:
         from .tips import pad_tips
 
