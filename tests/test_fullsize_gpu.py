@@ -76,3 +76,40 @@ def test_fullsize_properties(cuda, name):
     scale = dll.abs().max().item()
     np.testing.assert_allclose(dllp.cpu().numpy(), 2.0 * dll.cpu().numpy(), rtol=1e-9, atol=1e-11 * scale)
     ens_p.close()
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_fullsize_complete_units_match_oracle(cuda, name):
+    """>= 3 COMPLETE (tree, sample) units at each BASELINE full size: total log-likelihood, every per-site value and the
+    full d ll / d bl vector against the C/OpenMP port of prune.py (oracle/prune_ref.c; itself pinned to the reference's
+    source on small cases by tests/test_reference_pin.py and to the NumPy restatement by tests/test_oracle_selfcheck.py)."""
+    import oracle.cref as cref
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY
+    from vbsky_b200.synth import make_ensemble
+    from vbsky_b200.tips import PackedTips
+
+    T, n, S, K, clock = SHAPES[name]
+    T = min(T, 3)
+    Q = HKY(2.7)
+    data = make_ensemble(T, n, S, K, seed=3 + len(name), Q=Q, clock_rate=clock, device=cuda)
+    rng = np.random.default_rng(2)
+    counts = [rng.integers(0, 4, S).astype(np.float64) for _ in range(T)]
+    ens = Ensemble(data.tds, [PackedTips(t.patterns, c) for t, c in zip(data.tips, counts)], Q, device=cuda)
+    units = [(t, k) for t in range(T) for k in range(K)][:4] if T > 1 else [(0, 0), (0, 1)]
+    if len(units) < 3:  # config 2 has one tree: add a third sample of heights by perturbing the branch lengths
+        units.append((0, 0))
+    bl = np.stack([data.heights[t].branch_lengths[k] for t, k in units]) * clock
+    bl[-1] *= rng.uniform(0.7, 1.3, bl.shape[1])
+    ut = torch.as_tensor(np.array([t for t, _ in units], dtype=np.int32), device=cuda)
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), ut, want_grad=True, want_site_ll=True)
+    oQ = osub.HKY(2.7)
+    for u, (t, _) in enumerate(units):
+        td = data.tds[t]
+        otdd = otd.TreeData(td.postorder, td.child_parent, td.parent_child, td.sample_times)
+        ll_o, g_o, site_o = cref.prune(otdd, bl[u], oQ, data.tips[t].patterns, counts[t], want_grad=True, want_site_ll=True)
+        assert abs(ll[u].item() - ll_o) <= 1e-9 * abs(ll_o), (name, u)
+        # absolute floor on per-site values: the reference forms short-branch P(t) off-diagonals by cancellation (DESIGN.md section 3)
+        np.testing.assert_allclose(site[u].cpu().numpy(), site_o, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(dll[u].cpu().numpy(), g_o, rtol=1e-6, atol=1e-6 * np.abs(g_o).max())
+    ens.close()
