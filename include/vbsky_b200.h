@@ -144,6 +144,12 @@ int vbsky_layout_info(const vbsky_layout* lay, int32_t info[8]);
  * lower_sampling_times[2n-1], siblings[2n-1].  Any output may be NULL.                       */
 int vbsky_layout_get(const vbsky_layout* lay, int32_t t, int32_t* up, int32_t* down,
                      int32_t* down_nodes, double* lower_sampling_times, int32_t* siblings);
+/* The down pass's ring-stage chunking (inspection / tests): n_chunks, chunk_start[cap+1] (first step of each chunk;
+ * chunks hold <= 3 consecutive steps and never split a step from the cherry children it rebuilds), msg_start[cap+1]
+ * (prefix of msg_rows per chunk), n_msgs and msg_rows[max(n-2,1)] (scratch rows of the internal non-cherry children in
+ * consumption order).  cap = vbsky_layout_info()[5].  Any output may be NULL.                                    */
+int vbsky_layout_get_chunks(const vbsky_layout* lay, int32_t t, int32_t* n_chunks, int32_t* chunk_start,
+                            int32_t* msg_start, int32_t* n_msgs, int32_t* msg_rows);
 
 /* ------------------------------------------------------------------------------------------
  * Tip data of the ensemble on the device: TipData(partials[S,n,4], counts[S]) per tree

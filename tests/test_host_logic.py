@@ -167,7 +167,10 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
             carry = m
             if w & 32:
                 stack[(z >> 16) & 0xFF] = m
-            scratch[step] = m
+            is_cherry = a < n and b < n
+            assert bool(w & 0x40) == is_cherry
+            if not is_cherry:
+                scratch[step] = m  # a cherry's message never travels through scratch: the down pass rebuilds it
     up_row = {int(par): i for i, (_, par, _, _) in enumerate(up)}
     g = np.zeros((S, 2 * n - 2))
     Qm = Q.Q
@@ -181,8 +184,19 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
         pre = carry.copy() if w & 8 else stack[sp].copy()
         assert not np.isnan(pre).any()
         carry = np.full((S, 4), np.nan)
-        ma = Q.expm_action(bl[a], partials[:, a]) if w & 1 else scratch[up_row[a]]
-        mb = Q.expm_action(bl[b], partials[:, b]) if w & 2 else scratch[up_row[b]]
+        def rebuilt(child, rec):
+            # the cherry's own down-record follows: both children tips; message = expm_action(bl[c], normalised product)
+            (x2, par2, _, w2) = down[rec]
+            assert par2 == child and (w2 & 3) == 3
+            a2, b2 = x2 & 0xFFFF, (x2 >> 16) & 0xFFFF
+            pr = Q.expm_action(bl[a2], partials[:, a2]) * Q.expm_action(bl[b2], partials[:, b2])
+            return Q.expm_action(bl[child], pr / pr.sum(1, keepdims=True))
+
+        if w & 0x80:
+            assert w & 0x40, "b is rebuilt only when a is"
+        ma = Q.expm_action(bl[a], partials[:, a]) if w & 1 else (rebuilt(a, step + 1) if w & 0x40 else scratch[up_row[a]])
+        mb = Q.expm_action(bl[b], partials[:, b]) if w & 2 else (rebuilt(b, step + 2) if w & 0x80 else scratch[up_row[b]])
+        assert not np.isnan(ma).any() and not np.isnan(mb).any()
         # Q m_c: for tips the kernel uses (Q P(t)) e_mask with the unclipped message
         qa = (Q.expm(bl[a]) @ partials[:, a].T).T @ Qm.T if w & 1 else ma @ Qm.T
         qb = (Q.expm(bl[b]) @ partials[:, b].T).T @ Qm.T if w & 2 else mb @ Qm.T
@@ -198,6 +212,47 @@ def _interpret(up, down, dn, n, bl, Q, partials, depth):
             B = Q.expm_action(bl[b], wb, right=False)
             stack[(z >> 16) & 0xFF] = B / B.sum(1, keepdims=True)  # an internal b is parked
     return ll, g
+
+
+def _check_chunks(h, t, n, up, down):
+    """Ring-stage chunking of the down pass: chunks of <= 3 consecutive steps covering 0..n-2 that never split a step
+    from the cherry records it rebuilds from, and the message list = scratch rows of the internal non-cherry children."""
+    info = (C.c_int32 * 8)()
+    _lib.check(_lib.lib.vbsky_layout_info(h, info))
+    cap = info[5]
+    nch, nmsg = C.c_int32(), C.c_int32()
+    cstart = np.zeros(cap + 1, dtype=np.int32)
+    mstart = np.zeros(cap + 1, dtype=np.int32)
+    mrows = np.zeros(max(n - 2, 1), dtype=np.int32)
+    _lib.check(_lib.lib.vbsky_layout_get_chunks(h, t, C.byref(nch), _lib.np_ptr(cstart, C.c_int32), _lib.np_ptr(mstart, C.c_int32),
+                                                 C.byref(nmsg), _lib.np_ptr(mrows, C.c_int32)))
+    nch, nmsg = nch.value, nmsg.value
+    assert cstart[0] == 0 and cstart[nch] == n - 1 and mstart[0] == 0 and mstart[nch] == nmsg
+    sizes = np.diff(cstart[: nch + 1])
+    assert (sizes >= 1).all() and (sizes <= 3).all()
+    chunk_of = np.repeat(np.arange(nch), sizes)
+    up_row = {int(par): i for i, (_, par, _, _) in enumerate(up)}
+    want_rows = []
+    n_cherries = 0
+    for step, (x, par, z, w) in enumerate(down):
+        a, b = x & 0xFFFF, (x >> 16) & 0xFFFF
+        if w & 0x40:
+            assert chunk_of[step + 1] == chunk_of[step]
+            n_cherries += 1
+        elif not (w & 1):
+            want_rows.append(up_row[a])
+        if w & 0x80:
+            assert chunk_of[step + 2] == chunk_of[step]
+            n_cherries += 1
+        elif not (w & 2):
+            want_rows.append(up_row[b])
+    assert mrows[:nmsg].tolist() == want_rows
+    assert nmsg == (n - 2) - n_cherries
+    # per-chunk message counts match the prefix array
+    per_chunk = np.zeros(nch, dtype=int)
+    for step, (x, par, z, w) in enumerate(down):
+        per_chunk[chunk_of[step]] += int(not (w & 1) and not (w & 0x40)) + int(not (w & 2) and not (w & 0x80))
+    assert np.array_equal(np.diff(mstart[: nch + 1]), per_chunk)
 
 
 @pytest.mark.parametrize("n,caterpillar", [(2, False), (3, False), (7, False), (33, False), (64, True), (120, False)])
@@ -220,6 +275,7 @@ def test_schedules_reproduce_oracle(n, caterpillar):
         codes = evolve_codes(td, bl, Q, 40, rng, missing=0.1)
         partials = codes_to_partials(codes)
         ll, g = _interpret(up, down, dn, n, bl, Q, partials, depth)
+        _check_chunks(h, t, n, up, down)
         ll_o, g_o = oprune.prune_loglik_and_grad(bl, Q, partials, _o(td))
         np.testing.assert_allclose(ll, ll_o, rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(g, g_o, rtol=1e-9, atol=1e-9 * np.abs(g_o).max())

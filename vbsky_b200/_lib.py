@@ -75,6 +75,7 @@ SIGNATURES = {
     "vbsky_layout_destroy": (None, [_vp]),
     "vbsky_layout_info": (C.c_int, [_vp, _i32p]),
     "vbsky_layout_get": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _f64p, _i32p]),
+    "vbsky_layout_get_chunks": (C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "vbsky_tips_create": (C.c_int, [_vp, C.c_int64, _u8p, _f64p, C.POINTER(_vp)]),
     "vbsky_tips_destroy": (None, [_vp]),
     "vbsky_tips_set_counts": (C.c_int, [_vp, _f64p]),

@@ -41,13 +41,16 @@ int set_error(int code, const char* fmt, ...);
 //   x = a | b<<16, y = p, z = slotA | slotB<<8 | slotOut<<16 (shared-memory slots; 0xff = none),
 //   w = flags: bit0 a is a tip, bit1 b is a tip, bit2 p is the root, bit3 a is the result of the previous
 //   step (still in registers; the children are ordered so that only a ever is), bit5 the result must
-//   also be parked in slotOut.  The message produced by step s is streamed to scratch row s.
+//   also be parked in slotOut, bit6 p is a cherry (both children tips, not the root): its message is NOT
+//   streamed to scratch.  The message produced by any other step s is streamed to scratch row s.
 // One step of the down (preorder) pass: expand parent p into children a and b.
 //   x = a | b<<16, y = p, z = slotP | 0xff<<8 | slotB<<16, w = flags: bit0/bit1 tips as above,
 //   bit3 pre_p is carried in registers from the previous step -- for the root step, from the seed pi -- (else slotP).
 //   The children are ordered so that an internal a is expanded by the next step (its pre vector is
 //   carried) and an internal b is parked in slotB until the walk returns to it.
-//   Internal children's messages arrive through the message ring in the order a, b (h_msg_rows).
+//   Internal children's messages arrive through the message ring in the order a, b (h_msg_rows), except cherries:
+//   bit6 a is a cherry -- its message is rebuilt from the next record (a's own step), bit7 b is a cherry (then a is
+//   one too) -- rebuilt from the record after next; the chunking keeps those records in the same ring stage.
 struct Op {
   int32_t x, y, z, w;
 };
@@ -65,7 +68,11 @@ struct vbsky_layout {
   std::vector<vbsky::Op> h_up, h_down;        // [T][n-1]
   std::vector<int32_t> h_down_nodes;          // [T][2n-2]
   std::vector<int32_t> h_msg_rows;            // [T][n-2] scratch rows of internal children in down-pass consumption order
-  std::vector<int32_t> h_msg_start;           // [T][nchunks+1] prefix of h_msg_rows per chunk of kChunkSteps down steps
+  std::vector<int32_t> h_msg_start;           // [T][chunk_cap+1] prefix of h_msg_rows per down chunk
+  std::vector<int32_t> h_dchunk_start;        // [T][chunk_cap+1] first step of each (variable-length, <= kChunkSteps) down chunk
+  std::vector<int32_t> h_n_dchunks;           // [T] number of down chunks
+  std::vector<int32_t> h_n_msgs;              // [T] messages that travel through scratch (non-root internal nodes minus cherries)
+  int32_t chunk_cap = 0;
   std::vector<int32_t> h_child_parent;        // [T][N]
   std::vector<int32_t> h_parent_child;        // [T][N][2]
   std::vector<int32_t> h_siblings;            // [T][N]
@@ -80,6 +87,8 @@ struct vbsky_layout {
   int32_t* d_down_nodes = nullptr;
   int32_t* d_msg_rows = nullptr;
   int32_t* d_msg_start = nullptr;
+  int32_t* d_dchunk_start = nullptr;
+  int32_t* d_n_dchunks = nullptr;
   int32_t* d_child_parent = nullptr;
   int32_t* d_parent_child = nullptr;
   double* d_lst = nullptr;

@@ -46,9 +46,14 @@ struct SlotPool {
 
 // Build both schedules of one tree.  pc = parent_child [N][2].
 int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, int32_t* msg_rows,
-               int32_t* msg_start, int* depth_up, int* depth_down) {
+               int32_t* msg_start, int32_t* dchunk_start, int32_t* n_dchunks, int32_t* n_msgs, int* depth_up, int* depth_down) {
   const int N = 2 * n - 1, root = N - 1;
   auto internal = [n](int v) { return v >= n; };
+  // A "cherry" is a non-root internal node whose two children are tips.  Its message is cheap to recompute from the two
+  // tip tables (two gathers, a product and one 4x4 product per site), so the up pass does not stream it to scratch and
+  // the down pass rebuilds it at the parent's step from the cherry's own down-record, which the schedule places right
+  // after the parent's (same ring stage): about a third of all messages of a random tree never touch HBM.
+  auto cherry = [&](int v) { return v >= n && v != root && pc[2 * v] < n && pc[2 * v + 1] < n; };
 
   // ------------------------------------------------------------------------------------ up pass
   // need[v] = peak number of messages parked in shared memory while evaluating subtree v.  The message
@@ -125,6 +130,7 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
         if (src[k] == 1) flags |= 8 << k;
       }
       const int ca = ch[0], cb = ch[1], sa = slot[0], sb = slot[1];
+      if (cherry(v)) flags |= 0x40;  // message is not written to scratch
       if (v == root) {
         flags |= 4;
       } else if (up_row[parent[v]] != s + 1) {
@@ -152,8 +158,9 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
     else if (!ia && ib)
       needd[v] = needd[b], firstd[v] = 1;
     else {
-      // descend first into the child with the smaller need while the other's pre vector waits
-      const int f = needd[a] <= needd[b] ? 0 : 1;
+      // descend first into the child with the smaller need while the other's pre vector waits; a cherry always goes
+      // first (its need is 0, so this is never worse) so that its step directly follows the parent's
+      const int f = cherry(a) ? 0 : (cherry(b) ? 1 : (needd[a] <= needd[b] ? 0 : 1));
       const int cf = pc[2 * v + f], cs = pc[2 * v + 1 - f];
       needd[v] = std::max(needd[cf] + 1, needd[cs]);
       firstd[v] = f;
@@ -177,10 +184,20 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
   {
     SlotPool pool;
     std::fill(slot_of.begin(), slot_of.end(), -1);
-    int nmsg = 0;
+    int nmsg = 0, nchunk = 0, fill = 0;
+    // Ring stages hold up to kChunkSteps consecutive steps; a step and the cherry children it rebuilds (the next one or
+    // two steps) are never split across stages, so chunks have variable length.
+    auto group_size = [&](int v) { return 1 + (cherry(pc[2 * v]) ? 1 : 0) + (cherry(pc[2 * v + 1]) ? 1 : 0); };
     for (int s = 0; s < n - 1; ++s) {
       const int v = dorder[s];
-      if (s % kChunkSteps == 0) msg_start[s / kChunkSteps] = nmsg;
+      const bool member = cherry(v);  // belongs to its parent's group (already accounted for)
+      if (!member) {
+        const int g = group_size(v);
+        if (s == 0 || fill + g > kChunkSteps) {
+          dchunk_start[nchunk] = s, msg_start[nchunk] = nmsg, ++nchunk, fill = 0;
+        }
+        fill += g;
+      }
       int a = pc[2 * v + firstd[v]], b = pc[2 * v + 1 - firstd[v]];
       if (!internal(a) && internal(b)) std::swap(a, b);  // canonical: an internal a is expanded next (carried), an internal b is parked
       const int next = s + 1 < n - 1 ? dorder[s + 1] : -1;
@@ -195,11 +212,18 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
       }
       if (internal(a) && a != next) return set_error(VBSKY_EINVAL, "internal error: down schedule order");
       if (!internal(a)) flags |= 1;
+      else if (cherry(a)) flags |= 0x40;  // rebuilt from the next record
       else msg_rows[nmsg++] = up_row[a];
       if (!internal(b)) {
         flags |= 2;
       } else {
-        msg_rows[nmsg++] = up_row[b];
+        if (cherry(b)) {
+          // only reachable when a is a cherry too (a cherry always goes first): b's step is the one after a's
+          if (!cherry(a) || s + 2 >= n - 1 || dorder[s + 2] != b) return set_error(VBSKY_EINVAL, "internal error: cherry order");
+          flags |= 0x80;  // rebuilt from the record after next
+        } else {
+          msg_rows[nmsg++] = up_row[b];
+        }
         sb = pool.alloc();  // parked until the walk returns to it
         slot_of[b] = sb;
         if (sb >= 0xff) return set_error(VBSKY_EINVAL, "tree needs more than 254 live vectors");
@@ -208,7 +232,8 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
       down_nodes[2 * s] = a;
       down_nodes[2 * s + 1] = b;
     }
-    msg_start[(n - 1 + kChunkSteps - 1) / kChunkSteps] = nmsg;
+    dchunk_start[nchunk] = n - 1, msg_start[nchunk] = nmsg;
+    *n_dchunks = nchunk, *n_msgs = nmsg;
     *depth_down = std::max(pool.high, 1);
   }
   return VBSKY_OK;
@@ -242,6 +267,8 @@ extern "C" void vbsky_layout_destroy(vbsky_layout* lay) {
   cudaFree(lay->d_down_nodes);
   cudaFree(lay->d_msg_rows);
   cudaFree(lay->d_msg_start);
+  cudaFree(lay->d_dchunk_start);
+  cudaFree(lay->d_n_dchunks);
   cudaFree(lay->d_child_parent);
   cudaFree(lay->d_parent_child);
   cudaFree(lay->d_lst);
@@ -267,9 +294,13 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   lay->h_up.resize((size_t)T * (n - 1));
   lay->h_down.resize((size_t)T * (n - 1));
   lay->h_down_nodes.resize((size_t)T * (2 * n - 2));
-  const int nchunks = (n - 1 + kChunkSteps - 1) / kChunkSteps;
+  const int chunk_cap = n - 1;  // variable-length down chunks: at most one per step
+  lay->chunk_cap = chunk_cap;
   lay->h_msg_rows.assign((size_t)T * std::max(n - 2, 1), 0);
-  lay->h_msg_start.assign((size_t)T * (nchunks + 1), 0);
+  lay->h_msg_start.assign((size_t)T * (chunk_cap + 1), 0);
+  lay->h_dchunk_start.assign((size_t)T * (chunk_cap + 1), 0);
+  lay->h_n_dchunks.assign(T, 0);
+  lay->h_n_msgs.assign(T, 0);
   lay->h_child_parent.assign(child_parent, child_parent + (size_t)T * N);
   lay->h_parent_child.assign(parent_child, parent_child + (size_t)T * N * 2);
   lay->h_siblings.assign((size_t)T * N, -1);
@@ -307,7 +338,8 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
     int du = 0, dd = 0;
     rc = build_tree(n, pc, &lay->h_up[(size_t)t * (n - 1)], &lay->h_down[(size_t)t * (n - 1)],
                     &lay->h_down_nodes[(size_t)t * (2 * n - 2)], &lay->h_msg_rows[(size_t)t * std::max(n - 2, 1)],
-                    &lay->h_msg_start[(size_t)t * (nchunks + 1)], &du, &dd);
+                    &lay->h_msg_start[(size_t)t * (chunk_cap + 1)], &lay->h_dchunk_start[(size_t)t * (chunk_cap + 1)],
+                    &lay->h_n_dchunks[t], &lay->h_n_msgs[t], &du, &dd);
     if (rc != VBSKY_OK) break;
     lay->depth_up = std::max(lay->depth_up, du);
     lay->depth_down = std::max(lay->depth_down, dd);
@@ -372,6 +404,8 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   VB_UP(d_down_nodes, h_down_nodes)
   VB_UP(d_msg_rows, h_msg_rows)
   VB_UP(d_msg_start, h_msg_start)
+  VB_UP(d_dchunk_start, h_dchunk_start)
+  VB_UP(d_n_dchunks, h_n_dchunks)
   VB_UP(d_child_parent, h_child_parent)
   VB_UP(d_parent_child, h_parent_child)
   VB_UP(d_lst, h_lst)
@@ -388,6 +422,23 @@ extern "C" int vbsky_layout_info(const vbsky_layout* lay, int32_t info[8]) {
   VB_CHECK_ARG(lay && info, "NULL argument");
   std::memset(info, 0, 8 * sizeof(int32_t));
   info[0] = lay->T, info[1] = lay->n, info[2] = lay->depth_up, info[3] = lay->depth_down, info[4] = lay->max_levels;
+  info[5] = lay->chunk_cap;
+  long long tot = 0;
+  for (int v : lay->h_n_msgs) tot += v;
+  info[6] = (int32_t)(tot / std::max(lay->T, 1));  // mean number of messages per tree that travel through scratch
+  return VBSKY_OK;
+}
+
+extern "C" int vbsky_layout_get_chunks(const vbsky_layout* lay, int32_t t, int32_t* n_chunks, int32_t* chunk_start,
+                                       int32_t* msg_start, int32_t* n_msgs, int32_t* msg_rows) {
+  VB_CHECK_ARG(lay, "NULL layout");
+  VB_CHECK_ARG(t >= 0 && t < lay->T, "tree index %d out of range", t);
+  const int cap = lay->chunk_cap;
+  if (n_chunks) *n_chunks = lay->h_n_dchunks[t];
+  if (n_msgs) *n_msgs = lay->h_n_msgs[t];
+  if (chunk_start) std::memcpy(chunk_start, &lay->h_dchunk_start[(size_t)t * (cap + 1)], sizeof(int32_t) * (cap + 1));
+  if (msg_start) std::memcpy(msg_start, &lay->h_msg_start[(size_t)t * (cap + 1)], sizeof(int32_t) * (cap + 1));
+  if (msg_rows) std::memcpy(msg_rows, &lay->h_msg_rows[(size_t)t * std::max(lay->n - 2, 1)], sizeof(int32_t) * std::max(lay->n - 2, 1));
   return VBSKY_OK;
 }
 
