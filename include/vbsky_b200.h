@@ -291,6 +291,37 @@ int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips,
                                 double* ll_tree, double* ll_data, vbsky_param_grads* grads,
                                 void* ws, size_t ws_bytes, void* stream);
 
+/* Site-pattern-block sharding (north star: "the ensemble shards across trees and site-pattern blocks"; no counterpart
+ * in the reference).  When there are too few (tree, sample) units to fill the GPUs (one big tree, few samples), the ranks
+ * of a group evaluate the SAME units over disjoint ranges of 256-pattern tiles:
+ *   vbsky_tips_tiles                number of tiles per tree (ceil(S / 256));
+ *   vbsky_prune_value_and_grad_tiles  vbsky_prune_value_and_grad restricted to tiles [tile_begin, tile_end): ll and dll_dbl
+ *                                   are PARTIAL sums over those patterns (site_ll is written for them only);
+ *   vbsky_loglik_forward_partial    first half of vbsky_loglik_value_and_grad: height chain, tree prior (+ gradient),
+ *                                   data term over the tile range -> partial [ll_data (U) | d/d bl (U x (2n-2))] in ws;
+ *   vbsky_loglik_exchange_buffer    device pointer / length (doubles) of that contiguous region: sum it over the group
+ *                                   (one all-reduce, ~U * (2n-1) doubles) between the two halves;
+ *   vbsky_loglik_backward_complete  second half: combines the terms and runs the adjoint of the height chain.
+ * vbsky_loglik_value_and_grad is exactly forward_partial(all tiles) + backward_complete.                          */
+int32_t vbsky_tips_tiles(const vbsky_tips* tips);
+int vbsky_prune_value_and_grad_tiles(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                     const int32_t* unit_tree, const double* bl,
+                                     const vbsky_subst_model* model, int32_t tile_begin,
+                                     int32_t tile_end, double* site_ll, double* ll, double* dll_dbl,
+                                     void* ws, size_t ws_bytes, void* stream);
+int vbsky_loglik_forward_partial(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                 const int32_t* unit_tree, int32_t m, const vbsky_params* in,
+                                 const vbsky_subst_model* model, int32_t flags, int32_t tile_begin,
+                                 int32_t tile_end, int32_t want_grad, vbsky_param_grads* grads,
+                                 void* ws, size_t ws_bytes, void* stream);
+double* vbsky_loglik_exchange_buffer(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                     int32_t m, void* ws, int64_t* count);
+int vbsky_loglik_backward_complete(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                   const int32_t* unit_tree, int32_t m, const vbsky_params* in,
+                                   const vbsky_subst_model* model, int32_t flags, double* ll,
+                                   double* ll_tree, double* ll_data, vbsky_param_grads* grads,
+                                   void* ws, size_t ws_bytes, void* stream);
+
 /* The reduction step of one ensemble ELBO evaluation (no counterpart in the reference, which visits
  * trees one at a time, fasta.py:456-487): from the per-unit outputs of vbsky_loglik_value_and_grad build the payload
  * of the single all-reduce,

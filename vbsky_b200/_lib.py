@@ -103,6 +103,16 @@ SIGNATURES = {
     "vbsky_loglik_workspace_bytes": (C.c_size_t, [_vp, _vp, C.c_int32, C.c_int32]),
     "vbsky_loglik_value_and_grad": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), C.POINTER(SubstModel),
                                               C.c_int32, _vp, _vp, _vp, C.POINTER(ParamGrads), _vp, C.c_size_t, _vp]),
+    "vbsky_tips_tiles": (C.c_int32, [_vp]),
+    "vbsky_prune_value_and_grad_tiles": (
+        C.c_int,
+        [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, C.c_size_t, _vp],
+    ),
+    "vbsky_loglik_forward_partial": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), C.POINTER(SubstModel), C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_int32, C.POINTER(ParamGrads), _vp, C.c_size_t, _vp]),
+    "vbsky_loglik_exchange_buffer": (_vp, [_vp, _vp, C.c_int32, C.c_int32, _vp, _i64p]),
+    "vbsky_loglik_backward_complete": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Params), C.POINTER(SubstModel), C.c_int32,
+                                                 _vp, _vp, _vp, C.POINTER(ParamGrads), _vp, C.c_size_t, _vp]),
     "vbsky_reduce_elbo_count": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "vbsky_reduce_elbo": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.POINTER(ParamGrads), C.c_double, _vp, _vp]),
     "vbsky_session_create": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp)]),

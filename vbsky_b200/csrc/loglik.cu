@@ -16,6 +16,7 @@ __global__ void combine_kernel(int U, int flags, const double* lt, const double*
 
 struct LoglikPlan {
   size_t heights, bl, xs, times, lam, psi, mu, dbl, dxs, dtimes, dlam, dpsi, dmu, lt, ld, dh, bdsky, prune, total;
+  size_t xchg_count;  // doubles of the contiguous [ld (U) | dbl (U x (2n-2))] region: what site-block ranks add up
   size_t bdsky_bytes, prune_bytes;
 };
 
@@ -31,9 +32,13 @@ static int loglik_plan(const vbsky_layout* lay, const vbsky_tips* tips, int U, i
   const size_t d = sizeof(double);
   pl->heights = take(U * N * d), pl->bl = take(U * (N - 1) * d), pl->xs = take(U * N * d);
   pl->times = take(U * (mm + 1) * d), pl->lam = take(U * mm * d), pl->psi = take(U * mm * d), pl->mu = take(U * mm * d);
-  pl->dbl = take(U * (N - 1) * d), pl->dxs = take(U * N * d), pl->dtimes = take(U * (mm + 1) * d);
+  // the data term's partial results sit back to back so that one all-reduce covers them (site-pattern-block sharding)
+  pl->ld = off, off += U * d;
+  pl->dbl = take(U * (N - 1) * d);
+  pl->xchg_count = (size_t)U + (size_t)U * (N - 1);
+  pl->dxs = take(U * N * d), pl->dtimes = take(U * (mm + 1) * d);
   pl->dlam = take(U * mm * d), pl->dpsi = take(U * mm * d), pl->dmu = take(U * mm * d);
-  pl->lt = take(U * d), pl->ld = take(U * d), pl->dh = take(U * N * d);
+  pl->lt = take(U * d), pl->dh = take(U * N * d);
   pl->bdsky_bytes = vbsky_bdsky_workspace_bytes(U, lay->n);
   pl->bdsky = take(pl->bdsky_bytes);
   pl->prune_bytes = std::max(vbsky_prune_workspace_bytes(lay, tips, U, 1), vbsky_prune_workspace_bytes_f32(lay, tips, U, 1));
@@ -57,14 +62,12 @@ extern "C" size_t vbsky_loglik_workspace_bytes(const vbsky_layout* lay, const vb
   return pl.total;
 }
 
-extern "C" int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
-                                           const int32_t* unit_tree, int32_t m, const vbsky_params* in,
-                                           const vbsky_subst_model* model, int32_t flags, double* ll, double* ll_tree,
-                                           double* ll_data, vbsky_param_grads* grads, void* ws, size_t ws_bytes,
-                                           void* stream) {
-  VB_CHECK_ARG(lay && tips && unit_tree && in && model && ll && ws, "NULL argument");
+static int check_loglik_args(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, const int32_t* unit_tree, int32_t m,
+                             const vbsky_params* in, const vbsky_subst_model* model, int32_t flags, const vbsky_param_grads* grads,
+                             void* ws) {
+  VB_CHECK_ARG(lay && tips && unit_tree && in && model && ws, "NULL argument");
   VB_CHECK_ARG(U >= 1, "U must be >= 1");
-  const bool tree = flags & VBSKY_TERM_TREE, data = flags & VBSKY_TERM_DATA;
+  const bool tree = flags & VBSKY_TERM_TREE;
   // bdsky.py:282-284 shape asserts: one proportion per internal non-root node is implied by the [U][n-2] layout;
   // len(R) == len(s) == len(delta) == m is implied by the [U][m] layout.
   if (tree) VB_CHECK_ARG(m >= 1 && in->R && in->delta && in->s && in->rho, "the tree-prior term needs m >= 1 and R, delta, s, rho");
@@ -72,35 +75,79 @@ extern "C" int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_
     VB_CHECK_ARG((grads->proportions || lay->n == 2) && grads->root_proportion && grads->origin && grads->clock_rate, "NULL gradient output");
     if (tree) VB_CHECK_ARG(grads->R && grads->delta && grads->s && grads->rho, "NULL skyline gradient output");
   }
+  return VBSKY_OK;
+}
+
+// First half: height chain, tree prior (+ its gradient), data term over the tiles [tile_begin, tile_end) -> partial
+// [ld | dbl] in the workspace.
+extern "C" int vbsky_loglik_forward_partial(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, const int32_t* unit_tree,
+                                            int32_t m, const vbsky_params* in, const vbsky_subst_model* model, int32_t flags,
+                                            int32_t tile_begin, int32_t tile_end, int32_t want_grad, vbsky_param_grads* grads,
+                                            void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_loglik_args(lay, tips, U, unit_tree, m, in, model, flags, want_grad ? grads : nullptr, ws);
+  if (rc != VBSKY_OK) return rc;
+  if (want_grad) VB_CHECK_ARG(grads != nullptr, "grads is NULL");
+  const bool tree = flags & VBSKY_TERM_TREE, data = flags & VBSKY_TERM_DATA;
   LoglikPlan pl;
-  int rc = loglik_plan(lay, tips, U, m, &pl);
+  rc = loglik_plan(lay, tips, U, m, &pl);
   if (rc != VBSKY_OK) return rc;
   if (ws_bytes < pl.total) return set_error(VBSKY_ENOMEM, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total);
   char* b = (char*)ws;
   auto D = [&](size_t off) { return (double*)(b + off); };
   cudaStream_t st = (cudaStream_t)stream;
   const int n = lay->n;
-
   rc = vbsky_heights_forward(lay, U, unit_tree, tree ? m : 0, in, D(pl.heights), D(pl.bl), tree ? D(pl.xs) : nullptr,
                              tree ? D(pl.times) : nullptr, D(pl.lam), D(pl.psi), D(pl.mu), stream);
   if (rc != VBSKY_OK) return rc;
   if (tree) {
     rc = vbsky_bdsky_value_and_grad(U, n, m, D(pl.lam), D(pl.psi), D(pl.mu), in->rho, D(pl.xs), D(pl.times),
-                                    (flags & VBSKY_CONDITION_ON_SURVIVAL) ? 1 : 0, D(pl.lt), grads ? D(pl.dlam) : nullptr,
-                                    D(pl.dpsi), D(pl.dmu), grads ? grads->rho : nullptr, D(pl.dxs), D(pl.dtimes),
+                                    (flags & VBSKY_CONDITION_ON_SURVIVAL) ? 1 : 0, D(pl.lt), want_grad ? D(pl.dlam) : nullptr,
+                                    D(pl.dpsi), D(pl.dmu), want_grad ? grads->rho : nullptr, D(pl.dxs), D(pl.dtimes),
                                     b + pl.bdsky, pl.bdsky_bytes, stream);
     if (rc != VBSKY_OK) return rc;
-  } else if (grads && grads->rho && m >= 1) {
+  } else if (want_grad && grads->rho && m >= 1) {
     VB_CUDA(cudaMemsetAsync(grads->rho, 0, (size_t)U * m * sizeof(double), st));
   }
   if (data) {
+    if (flags & VBSKY_PRUNE_F32) VB_CHECK_ARG(tile_begin == 0 && tile_end == tips->tiles, "the fp32 data term does not take a tile sub-range");
     rc = (flags & VBSKY_PRUNE_F32)
              ? vbsky_prune_value_and_grad_f32(lay, tips, U, unit_tree, D(pl.bl), model, nullptr, D(pl.ld),
-                                              grads ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream)
-             : vbsky_prune_value_and_grad(lay, tips, U, unit_tree, D(pl.bl), model, nullptr, D(pl.ld),
-                                          grads ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream);
+                                              want_grad ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream)
+             : vbsky_prune_value_and_grad_tiles(lay, tips, U, unit_tree, D(pl.bl), model, tile_begin, tile_end, nullptr, D(pl.ld),
+                                                want_grad ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream);
     if (rc != VBSKY_OK) return rc;
   }
+  return VBSKY_OK;
+}
+
+extern "C" double* vbsky_loglik_exchange_buffer(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, int32_t m, void* ws,
+                                                int64_t* count) {
+  LoglikPlan pl;
+  if (!lay || !tips || !ws || U < 1 || loglik_plan(lay, tips, U, m, &pl) != VBSKY_OK) {
+    set_error(VBSKY_EINVAL, "bad argument to vbsky_loglik_exchange_buffer");
+    return nullptr;
+  }
+  if (count) *count = (int64_t)pl.xchg_count;
+  return (double*)((char*)ws + pl.ld);
+}
+
+// Second half: combine the terms and run the adjoint of the height chain on the (complete) [ld | dbl].
+extern "C" int vbsky_loglik_backward_complete(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, const int32_t* unit_tree,
+                                              int32_t m, const vbsky_params* in, const vbsky_subst_model* model, int32_t flags,
+                                              double* ll, double* ll_tree, double* ll_data, vbsky_param_grads* grads, void* ws,
+                                              size_t ws_bytes, void* stream) {
+  int rc = check_loglik_args(lay, tips, U, unit_tree, m, in, model, flags, grads, ws);
+  if (rc != VBSKY_OK) return rc;
+  VB_CHECK_ARG(ll != nullptr, "ll is NULL");
+  const bool tree = flags & VBSKY_TERM_TREE, data = flags & VBSKY_TERM_DATA;
+  LoglikPlan pl;
+  rc = loglik_plan(lay, tips, U, m, &pl);
+  if (rc != VBSKY_OK) return rc;
+  if (ws_bytes < pl.total) return set_error(VBSKY_ENOMEM, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total);
+  char* b = (char*)ws;
+  auto D = [&](size_t off) { return (double*)(b + off); };
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = lay->n;
   combine_kernel<<<(U + 127) / 128, 128, 0, st>>>(U, flags, D(pl.lt), D(pl.ld), ll, ll_tree, ll_data);
   VB_CUDA(cudaGetLastError());
   if (grads) {
@@ -118,4 +165,16 @@ extern "C" int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_
     }
   }
   return VBSKY_OK;
+}
+
+extern "C" int vbsky_loglik_value_and_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                           const int32_t* unit_tree, int32_t m, const vbsky_params* in,
+                                           const vbsky_subst_model* model, int32_t flags, double* ll, double* ll_tree,
+                                           double* ll_data, vbsky_param_grads* grads, void* ws, size_t ws_bytes,
+                                           void* stream) {
+  VB_CHECK_ARG(ll != nullptr, "NULL argument");
+  int rc = vbsky_loglik_forward_partial(lay, tips, U, unit_tree, m, in, model, flags, 0, tips ? tips->tiles : 0, grads != nullptr,
+                                        grads, ws, ws_bytes, stream);
+  if (rc != VBSKY_OK) return rc;
+  return vbsky_loglik_backward_complete(lay, tips, U, unit_tree, m, in, model, flags, ll, ll_tree, ll_data, grads, ws, ws_bytes, stream);
 }

@@ -185,6 +185,20 @@ extern "C" int vbsky_prune_value_and_grad(const vbsky_layout* lay, const vbsky_t
                                           double* dll_dbl, void* ws, size_t ws_bytes, void* stream) {
   return f64::run(lay, tips, U, unit_tree, bl, model, site_ll, ll, dll_dbl, ws, ws_bytes, stream);
 }
+extern "C" int32_t vbsky_tips_tiles(const vbsky_tips* tips) {
+  if (!tips) {
+    set_error(VBSKY_EINVAL, "NULL tips");
+    return -1;
+  }
+  return tips->tiles;
+}
+extern "C" int vbsky_prune_value_and_grad_tiles(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                                                const int32_t* unit_tree, const double* bl, const vbsky_subst_model* model,
+                                                int32_t tile_begin, int32_t tile_end, double* site_ll, double* ll,
+                                                double* dll_dbl, void* ws, size_t ws_bytes, void* stream) {
+  VB_CHECK_ARG(tile_begin >= 0 && tile_end > tile_begin, "bad tile range [%d, %d)", tile_begin, tile_end);
+  return f64::run(lay, tips, U, unit_tree, bl, model, site_ll, ll, dll_dbl, ws, ws_bytes, stream, nullptr, tile_begin, tile_end);
+}
 extern "C" int vbsky_prune_spectral_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, const int32_t* unit_tree,
                                          const double* bl, const vbsky_subst_model* model, const double* g, double* ll,
                                          double* out, void* ws, size_t ws_bytes, void* stream) {

@@ -105,7 +105,7 @@ class Ensemble:
         return self._ws
 
     def prune(self, bl: torch.Tensor, unit_tree: torch.Tensor, want_grad: bool = True, want_site_ll: bool = False,
-              precision: str = "f64"):
+              precision: str = "f64", tile_range=None):
         """bl [U, 2n-2] fp64 (already multiplied by the clock rate), unit_tree [U] int32, both on the
         device.  Returns (ll [U], dll_dbl [U, 2n-2] or None, site_ll [U, S] or None).
         ``precision="f32"`` runs the fp32-storage kernels (inputs/outputs stay fp64; 1e-5 tolerance)."""
@@ -128,9 +128,18 @@ class Ensemble:
             dll = torch.empty(U, 2 * self.n - 2, dtype=torch.float64, device=self.device) if want_grad else None
             site = torch.empty(U, self.S, dtype=torch.float64, device=self.device) if want_site_ll else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(f_run(
-                self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model),
-                _ptr(site), _ptr(ll), _ptr(dll), _ptr(ws), ws.numel(), C.c_void_p(stream)))
+            if tile_range is not None:
+                if precision != "f64":
+                    raise ValueError("tile ranges are an fp64 feature")
+                if site is not None:
+                    site.zero_()  # only the range's patterns are written
+                _lib.check(_lib.lib.vbsky_prune_value_and_grad_tiles(
+                    self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model), int(tile_range[0]), int(tile_range[1]),
+                    _ptr(site), _ptr(ll), _ptr(dll), _ptr(ws), ws.numel(), C.c_void_p(stream)))
+            else:
+                _lib.check(f_run(
+                    self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model),
+                    _ptr(site), _ptr(ll), _ptr(dll), _ptr(ws), ws.numel(), C.c_void_p(stream)))
         return ll, dll, site
 
     def prune_spectral_grad(self, bl: torch.Tensor, unit_tree: torch.Tensor, g):
@@ -198,11 +207,21 @@ class Ensemble:
     GRAD_KEYS = ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho")
     PARAM_KEYS = ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho")
 
+    @property
+    def tiles(self) -> int:
+        """Number of 256-pattern tiles per tree (the granularity of site-pattern-block sharding)."""
+        return int(_lib.lib.vbsky_tips_tiles(self._tips))
+
     def loglik_device(self, params: dict, unit_tree: torch.Tensor, m: int, flags: int = 7, grads: Optional[dict] = None,
-                      out: Optional[dict] = None):
+                      out: Optional[dict] = None, tile_range=None, exchange=None):
         """Raw device call of vbsky_loglik_value_and_grad (no autograd): ``params`` / ``grads`` map the
         vbsky_params / vbsky_param_grads field names to contiguous CUDA fp64 tensors ([U, ...]); ``out``
-        may provide preallocated 'll', 'tree', 'data' [U] tensors.  Returns ``out``."""
+        may provide preallocated 'll', 'tree', 'data' [U] tensors.  Returns ``out``.
+
+        Site-pattern-block sharding: ``tile_range=(begin, end)`` evaluates the data term over those 256-pattern tiles only
+        (``vbsky_loglik_forward_partial``), then ``exchange(buf)`` is called with the contiguous fp64 tensor
+        [ll_data (U) | d/d bl (U x (2n-2))] -- sum it over the ranks that share these units, in place (one all-reduce) --
+        and ``vbsky_loglik_backward_complete`` finishes the evaluation."""
         U = unit_tree.shape[0]
         cin = _lib.Params()
         for k in self.PARAM_KEYS:
@@ -224,7 +243,24 @@ class Ensemble:
                 raise _lib.VbskyError(-1, _lib.last_error())
             ws = self._workspace(need)
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(_lib.lib.vbsky_loglik_value_and_grad(
+            if tile_range is None:
+                _lib.check(_lib.lib.vbsky_loglik_value_and_grad(
+                    self._layout, self._tips, U, _ptr(unit_tree), m, C.byref(cin), C.byref(self._model), flags,
+                    _ptr(out["ll"]), _ptr(out["tree"]), _ptr(out["data"]), None if cg is None else C.byref(cg),
+                    _ptr(ws), ws.numel(), C.c_void_p(stream)))
+                return out
+            _lib.check(_lib.lib.vbsky_loglik_forward_partial(
+                self._layout, self._tips, U, _ptr(unit_tree), m, C.byref(cin), C.byref(self._model), flags,
+                int(tile_range[0]), int(tile_range[1]), int(cg is not None), None if cg is None else C.byref(cg),
+                _ptr(ws), ws.numel(), C.c_void_p(stream)))
+            if exchange is not None:
+                cnt = C.c_int64(0)
+                ptr = _lib.lib.vbsky_loglik_exchange_buffer(self._layout, self._tips, U, m, _ptr(ws), C.byref(cnt))
+                if not ptr:
+                    raise _lib.VbskyError(-1, _lib.last_error())
+                off = ptr - ws.data_ptr()
+                exchange(ws[off: off + 8 * cnt.value].view(torch.float64))
+            _lib.check(_lib.lib.vbsky_loglik_backward_complete(
                 self._layout, self._tips, U, _ptr(unit_tree), m, C.byref(cin), C.byref(self._model), flags,
                 _ptr(out["ll"]), _ptr(out["tree"]), _ptr(out["data"]), None if cg is None else C.byref(cg),
                 _ptr(ws), ws.numel(), C.c_void_p(stream)))

@@ -26,6 +26,21 @@ def shard_units(T: int, K: int, rank: int, world: int) -> List[Tuple[int, int]]:
     return [(u // K, u % K) for u in range(rank, T * K, world)]
 
 
+def shard_plan(U: int, tiles: int, world: int, min_units_per_rank: int = 16) -> Tuple[int, int]:
+    """(ranks over units, ranks over site-pattern blocks) for ``world`` GPUs.  Units shard without any exchange, so they
+    are preferred whenever every rank still gets a reasonable number of them; otherwise (one big tree, few samples: the
+    config-2 shape) every rank evaluates ALL units over its own contiguous range of 256-pattern tiles and the per-unit
+    partial results [ll_data, d/d bl] are summed by one extra all-reduce inside the step."""
+    if world == 1 or U >= min_units_per_rank * world or tiles < world:
+        return world, 1
+    return 1, world
+
+
+def tile_range(tiles: int, part: int, parts: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``tiles`` 256-pattern blocks: the range owned by ``part`` of ``parts``."""
+    return (tiles * part) // parts, (tiles * (part + 1)) // parts
+
+
 def payload_count(T: int, n: int, m: int) -> int:
     return 3 + 4 * m + T * (n - 1)
 
