@@ -208,6 +208,19 @@ int vbsky_prune_spectral_grad(const vbsky_layout* lay, const vbsky_tips* tips, i
                               const vbsky_subst_model* model, const double* g, double* ll,
                               double* out, void* ws, size_t ws_bytes, void* stream);
 
+/* Gradient w.r.t. an ARBITRARY parameter theta of the substitution model (north star item 3; the reference drops
+ * these tangents, prune.py:149).  dQ [16] = dQ/dtheta (row-major; any direction, need not commute with Q: base
+ * frequencies of HKY/GTR, GTR exchangeabilities).  One evaluation of the pruning kernel with a per-branch matrix in
+ * eq. (9)'s quadratic form, D_b = dP(t_b)/dtheta P(t_b)^-1:
+ *   out[u][b] = sum_s counts[s] * (w^T D_b m_b) / (w^T m_b)   -- branch b's contribution,
+ *   d ll[u] / d theta (Q-part) = sum_b out[u][b]              (no branch-length factor),
+ * dpi [U][4] (may be NULL) = d ll[u] / d pi_i at fixed Q (the root-frequency term of prune.py:131); the caller adds
+ * sum_i dpi[u][i] * d pi_i / d theta.  Workspace as vbsky_prune_workspace_bytes(..., want_grad = 1).  fp64 only.   */
+int vbsky_prune_param_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U,
+                           const int32_t* unit_tree, const double* bl,
+                           const vbsky_subst_model* model, const double* dQ, double* ll,
+                           double* out, double* dpi, void* ws, size_t ws_bytes, void* stream);
+
 /* Counters of the last prune call made by this thread: out[0]=kernel launches,
  * out[1]=persistent CTAs, out[2]=sites per CTA tile, out[3]=dynamic smem bytes per CTA,
  * out[4]=algorithmic HBM bytes of the fused pruning kernel (DESIGN.md formula).               */
@@ -217,7 +230,8 @@ int vbsky_prune_last_stats(int64_t out[8]);
  * Model parameters of bdsky.loglik (bdsky.py:268-345), one row per unit, all device pointers:
  * the reference's `params` dict after optim.unpack (optim.py:19-32), vmapped over the sample
  * axis (optim.py:72).  proportions [U][n-2]; root_proportion, origin, origin_start, clock_rate
- * [U]; R, delta, s, rho [U][m].                                                              */
+ * [U]; R, delta, s, rho [U][m]; grid [U][m+1] (optional, see below).  Zero-initialise the struct: fields may be
+ * appended.                                                                                   */
 typedef struct vbsky_params {
   const double* proportions;
   const double* root_proportion;
@@ -228,6 +242,9 @@ typedef struct vbsky_params {
   const double* delta;
   const double* s;
   const double* rho;
+  /* Prespecified skyline grid (bdsky.py:317-319, equidistant_intervals=False): [U][m+1] or NULL.  When given,
+   * times = tm - grid with times[0] = 0 instead of linspace(0, tm, m+1).                                       */
+  const double* grid;
 } vbsky_params;
 
 /* Gradients w.r.t. the same fields (origin_start shares origin's gradient; both enter as a sum).
@@ -241,6 +258,7 @@ typedef struct vbsky_param_grads {
   double* delta;
   double* s;
   double* rho;
+  double* grid; /* [U][m+1] or NULL; entry 0 is always 0 (times[0] is pinned to 0) */
 } vbsky_param_grads;
 
 /* TreeData.height_transform (tree_data.py:287-367) and the glue of bdsky.loglik

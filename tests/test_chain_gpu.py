@@ -75,7 +75,7 @@ def test_loglik_matches_oracle(cuda, n, m, S, rho_last):
     unit_tree = torch.tensor([t for t, _ in plist], dtype=torch.int32, device=cuda)
     for c in [(False, True, True), (False, True, False), (False, False, True)]:
         params = {k: torch.tensor(np.stack([p[k] for _, p in plist]), device=cuda, requires_grad=(k != "origin_start"))
-                  for k in bdsky.PARAM_KEYS}
+                  for k in bdsky.PARAM_KEYS if k != "grid"}
         ll, parts = bdsky.loglik(params, ens, unit_tree, c=c, return_parts=True)
         ll.sum().backward()
         for u, (t, p) in enumerate(plist):
@@ -165,4 +165,64 @@ def test_golden_fixture_from_reference_sims(cuda, kind):
     np.testing.assert_allclose(site[0].cpu().numpy(), np.array(g["site_ll"]), rtol=1e-9, atol=1e-13)
     want = np.array(g["dll_dbl"])
     np.testing.assert_allclose(dll[0].cpu().numpy(), want, rtol=1e-6, atol=1e-6 * np.abs(want).max())
+    ens.close()
+
+
+@pytest.mark.parametrize("n,m,S", [(6, 4, 64), (25, 10, 120)])
+def test_loglik_prespecified_grid_matches_oracle(cuda, n, m, S):
+    """equidistant_intervals=False (bdsky.py:317-319): times = tm - grid with times[0] = 0, through the FUSED entry point
+    and through the host-buffer entry point; value, every gradient incl. d/d origin (which now flows through
+    times = tm - grid) and d/d grid, against the oracle (pinned to the reference in tests/test_reference_pin.py)."""
+    from vbsky_b200 import bdsky
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY, codes_to_partials
+    from vbsky_b200.synth import evolve_codes, random_tree
+    from vbsky_b200.tips import PackedTips, compress_patterns, pad_tips
+
+    rng = np.random.default_rng(n + 100 * m)
+    T, K = 2, 2
+    Q, oQ = HKY(2.7), osub.HKY(2.7)
+    tds, tips, otips_ = [], [], []
+    for t in range(T):
+        td = random_tree(n, rng)
+        codes = evolve_codes(td, np.full(2 * n - 2, 0.05), oQ, S, rng, missing=0.05)
+        pat, cnt = compress_patterns(codes)
+        tds.append(td), tips.append(PackedTips(pat, cnt.astype(float)))
+        otips_.append(TipData(codes_to_partials(pat), cnt.astype(float)))
+    padded = pad_tips(tips)
+    ens = Ensemble(tds, padded, Q, device=cuda)
+    plist = []
+    for t in range(T):
+        for p in _rand_params(tds[t], m, rng, K):
+            tm = p["origin"][0] + p["origin_start"][0]
+            # a decreasing grid of calendar-style change points: grid[0] is ignored by the reference (times[0] := 0)
+            p["grid"] = np.concatenate([[tm * 1.3], np.sort(rng.uniform(0.03 * tm, 0.97 * tm, m - 1))[::-1], [0.0]])
+            plist.append((t, p))
+    unit_tree = torch.tensor([t for t, _ in plist], dtype=torch.int32, device=cuda)
+    keys = [k for k in bdsky.PARAM_KEYS]
+    for c in [(False, True, True), (False, True, False)]:
+        params = {k: torch.tensor(np.stack([p[k] for _, p in plist]), device=cuda, requires_grad=(k != "origin_start")) for k in keys}
+        ll = bdsky.loglik(params, ens, unit_tree, c=c, equidistant_intervals=False)
+        ll.sum().backward()
+        for u, (t, p) in enumerate(plist):
+            tp = {k: torch.tensor(v, requires_grad=True) for k, v in p.items()}
+            o = obdsky.loglik(tp, _o(tds[t]), otips_[t], oQ, c=c, equidistant_intervals=False)
+            o.backward()
+            assert abs(ll[u].item() - o.item()) <= 1e-9 * abs(o.item()), (c, u)
+            for k in ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "grid"):
+                want = tp[k].grad.numpy().reshape(-1) if tp[k].grad is not None else np.zeros(p[k].size)
+                got = params[k].grad[u].cpu().numpy().reshape(-1)
+                if want.size:
+                    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6 * max(np.abs(want).max(), 1e-12), err_msg=f"{c} {u} {k}")
+    # the equidistant evaluation of the same parameters differs (the grid is really used) ...
+    eq = bdsky.loglik({k: v.detach() for k, v in params.items() if k != "grid"}, ens, unit_tree, c=(False, True, False))
+    assert not torch.allclose(eq, ll.detach(), rtol=1e-6)
+    # ... and the host-buffer entry point takes the grid as well
+    host = {k: np.ascontiguousarray(np.stack([p[k] for _, p in plist]).reshape(len(plist), -1)) for k in keys}
+    for k in ("root_proportion", "origin", "origin_start", "clock_rate"):
+        host[k] = host[k].reshape(-1)
+    hg = {k: np.empty_like(host[k]) for k in Ensemble.GRAD_KEYS + ("grid",)}
+    out = ens.loglik_host(host, unit_tree.cpu().numpy(), m, flags=1 | 4, grads=hg)
+    np.testing.assert_allclose(out["ll"], ll.detach().cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(hg["grid"], params["grid"].grad.cpu().numpy(), rtol=1e-10, atol=1e-12)
     ens.close()

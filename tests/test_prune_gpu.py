@@ -333,3 +333,62 @@ def test_kappa_gradient_matches_finite_differences(cuda, T, n, S, K, kappa, cloc
     assert got[0] == pytest.approx(fd_or, rel=1e-6, abs=1e-6 * scale)
     # closed-form spectrum derivative vs a difference of the model's own eigenvalues
     assert np.allclose(HKY_dkappa(kappa), (HKY(kappa + h).d - HKY(kappa - h).d) / (2 * h), rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("T,n,S,K,clock", [(2, 9, 300, 2, 0.05), (1, 40, 700, 2, 0.02)])
+def test_gtr_parameter_gradients_match_finite_differences(cuda, T, n, S, K, clock):
+    """d ll / d theta for every parameter of a GTR model with non-uniform base frequencies -- the six exchangeabilities
+    and the three free frequencies, i.e. directions dQ/dtheta that do NOT commute with Q (north star item 3; unsupported
+    in the reference, prune.py:149).  vbsky_prune_param_grad: one kernel evaluation per direction with the per-branch
+    matrix D_b = dP_b/dtheta P_b^-1 in eq. (9)'s quadratic form, plus the root-frequency term.  Pinned by central
+    differences of the fp64 oracle (NumPy restatement of prune.py) and of the kernel's own value path."""
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import GTR, codes_to_partials, gtr_directions, gtr_rate_matrix
+    from vbsky_b200.synth import make_ensemble
+
+    rates = np.array([0.9, 2.6, 0.7, 1.2, 3.1, 1.0])
+    pi = np.array([0.31, 0.19, 0.23, 0.27])
+    scale = 1.0 / -(pi * np.diag(gtr_rate_matrix(rates, pi))).sum()  # mean rate 1 at the evaluation point
+    rates = rates * scale
+    Q = GTR(rates, pi)
+    data = make_ensemble(T, n, S, K, seed=n + S, Q=Q, clock_rate=clock, missing=0.05)
+    bl = np.stack([data.heights[t].branch_lengths[k] for t in range(T) for k in range(K)]) * data.clock_rate
+    unit_tree = np.repeat(np.arange(T, dtype=np.int32), K)
+    bl_d, ut_d = torch.as_tensor(bl, device=cuda), torch.as_tensor(unit_tree, device=cuda)
+    ens = Ensemble(data.tds, data.tips, Q, device=cuda)
+    ll0, dll0, _ = ens.prune(bl_d, ut_d)
+    # with dQ = Q the per-branch matrix is t_b Q: the branch-length gradient times the branch length
+    ll1, tot1, out1, dpi1 = ens.prune_param_grad(bl_d, ut_d, Q.Q)
+    assert torch.equal(ll0, ll1)
+    np.testing.assert_allclose(out1.cpu().numpy(), (dll0 * bl_d).cpu().numpy(), rtol=1e-9, atol=1e-10 * (dll0 * bl_d).abs().max().item())
+    td = _oracle_td(data.tds[0])
+    part = codes_to_partials(data.tips[0].patterns)
+
+    def oracle_model(r, p):
+        m = GTR(r, p)
+        return osub.SubstitutionModel(m.pi, m.P, m.d, m.Pinv)
+
+    def value_gpu(r, p):
+        e = Ensemble(data.tds, data.tips, GTR(r, p), device=cuda)
+        v = e.prune(bl_d, ut_d, want_grad=False)[0].cpu().numpy()
+        e.close()
+        return v
+
+    value_or = lambda r, p: oprune.data_loglik_and_grad(bl[0], oracle_model(r, p), part, data.tips[0].counts, td)[0]
+    h = 1e-5
+    for k, (name, dQ, dpi) in enumerate(gtr_directions(rates, pi)):
+        _, got, _, _ = ens.prune_param_grad(bl_d, ut_d, dQ, dpi_dtheta=dpi)
+        got = got.cpu().numpy()
+        if k < 6:
+            rp, rm = rates.copy(), rates.copy()
+            rp[k] += h
+            rm[k] -= h
+            args_p, args_m = (rp, pi), (rm, pi)
+        else:
+            args_p, args_m = (rates, pi + h * dpi), (rates, pi - h * dpi)
+        fd_gpu = (value_gpu(*args_p) - value_gpu(*args_m)) / (2 * h)
+        fd_or = (value_or(*args_p) - value_or(*args_m)) / (2 * h)
+        sc = max(np.abs(fd_gpu).max(), 1e-8)
+        np.testing.assert_allclose(got, fd_gpu, rtol=2e-6, atol=2e-6 * sc, err_msg=name)
+        assert got[0] == pytest.approx(fd_or, rel=2e-6, abs=2e-6 * sc), name
+    ens.close()

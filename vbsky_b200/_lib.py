@@ -36,13 +36,13 @@ class SubstModel(C.Structure):
 class Params(C.Structure):
     """vbsky_params: device pointers, one row per unit."""
 
-    _fields_ = [(k, C.c_void_p) for k in ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho")]
+    _fields_ = [(k, C.c_void_p) for k in ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho", "grid")]
 
 
 class ParamGrads(C.Structure):
     """vbsky_param_grads."""
 
-    _fields_ = [(k, C.c_void_p) for k in ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho")]
+    _fields_ = [(k, C.c_void_p) for k in ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho", "grid")]
 
 
 _vp = C.c_void_p
@@ -61,6 +61,7 @@ SIGNATURES = {
     "vbsky_subst_rate_matrix": (C.c_int, [C.POINTER(SubstModel), _f64p]),
     "vbsky_hky_dkappa": (C.c_int, [C.c_double, _f64p]),
     "vbsky_prune_spectral_grad": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _f64p, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vbsky_prune_param_grad": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, C.POINTER(SubstModel), _f64p, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vbsky_encode_tips": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _u8p]),
     "vbsky_compress_patterns": (C.c_int, [_u8p, C.c_int64, C.c_int64, _i64p, _u8p, _i64p, _i64p]),
     "vbsky_encode_tips_device": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _i64p, _vp]),

@@ -15,8 +15,8 @@ import torch
 from . import _lib
 
 TERM_TREE, TERM_DATA, CONDITION_ON_SURVIVAL = 1, 2, 4
-PARAM_KEYS = ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho")
-GRAD_KEYS = ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho")
+PARAM_KEYS = ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho", "grid")
+GRAD_KEYS = ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho", "grid")
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -119,7 +119,8 @@ class _Loglik(torch.autograd.Function):
 
 
 def loglik(params: Dict[str, torch.Tensor], ens, unit_tree: torch.Tensor, c=(True, True, True),
-           condition_on_survival: bool = True, params_prior_loglik=None, return_parts: bool = False, clean: bool = False):
+           condition_on_survival: bool = True, params_prior_loglik=None, return_parts: bool = False, clean: bool = False,
+           equidistant_intervals: bool = True):
     """bdsky.loglik for U units.  ``params`` holds CUDA fp64 tensors with a leading unit axis:
     proportions [U, n-2], root_proportion/origin/origin_start/clock_rate [U] (or [U, 1]), R/delta/s/rho
     [U, m]; ``ens`` is the device-resident ``Ensemble``; ``unit_tree`` [U] int32 picks each unit's tree.
@@ -127,12 +128,15 @@ def loglik(params: Dict[str, torch.Tensor], ens, unit_tree: torch.Tensor, c=(Tru
     the prior term is the user's ``params_prior_loglik(params)`` -> [U] evaluated in torch.
     ``clean=True`` applies ``nan_to_num`` to every unit's value and gradient rows, which is what the reference's ``step``
     does to each single-sample (f, g) before averaging (fasta.py:421), so one non-finite draw is dropped, not spread.
-    Only equidistant skyline intervals (the reference's default, bdsky.py:314) are supported here."""
+    ``equidistant_intervals=False`` takes the prespecified grid ``params["grid"]`` [U, m+1] (bdsky.py:317-319:
+    ``times = tm - grid`` with ``times[0] = 0``) instead of ``linspace(0, tm, m+1)``; it is differentiable too."""
     U = unit_tree.shape[0]
     n = ens.n
     flat = {}
     for k in PARAM_KEYS:
-        v = params.get(k)
+        v = params.get(k) if (k != "grid" or not equidistant_intervals) else None
+        if k == "grid" and not equidistant_intervals and v is None:
+            raise ValueError("equidistant_intervals=False needs params['grid'] [U, m+1]")
         if v is None:
             flat[k] = None
             continue

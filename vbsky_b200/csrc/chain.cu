@@ -43,12 +43,13 @@ struct ChainParams {
   int n, m, max_levels, U;
   // inputs [U][...]
   const double *proportions, *root_proportion, *origin, *origin_start, *clock_rate, *R, *delta, *s;
+  const double* grid;  // [U][m+1] or null (equidistant skyline intervals)
   // forward outputs
   double *heights, *bl_scaled, *xs, *times, *lam, *psi, *mu;
   // backward inputs (any may be null => treated as zero)
   const double *d_bl, *d_xs, *d_times, *d_lam, *d_psi, *d_mu;
   // backward outputs
-  double *g_proportions, *g_root_proportion, *g_origin, *g_clock_rate, *g_R, *g_delta, *g_s;
+  double *g_proportions, *g_root_proportion, *g_origin, *g_clock_rate, *g_R, *g_delta, *g_s, *g_grid;
   double* dh;  // workspace [U][N]
 };
 
@@ -89,7 +90,13 @@ __global__ void __launch_bounds__(CT) chain_forward_kernel(const ChainParams p) 
   if (p.times) {
     double* times = p.times + (size_t)u * (m + 1);
     // jnp.linspace(0, tm, m+1): 0*(1-i/m) + tm*(i/m) for i < m, endpoint exactly tm (bdsky.py:316)
-    for (int i = tid; i <= m; i += CT) times[i] = i < m ? tm * ((double)i / (double)m) : tm;
+    if (p.grid) {
+      // prespecified grid (bdsky.py:317-319): times = tm - grid, times[0] = 0
+      const double* grid = p.grid + (size_t)u * (m + 1);
+      for (int i = tid; i <= m; i += CT) times[i] = i == 0 ? 0.0 : tm - grid[i];
+    } else {
+      for (int i = tid; i <= m; i += CT) times[i] = i < m ? tm * ((double)i / (double)m) : tm;
+    }
     for (int i = tid; i < m; i += CT) {
       const double d = p.delta[(size_t)u * m + i];
       const double psi = p.s[(size_t)u * m + i] * d;
@@ -121,8 +128,19 @@ __global__ void __launch_bounds__(CT) chain_backward_kernel(const ChainParams p)
     if (dbl && c < N - 1) acc_clock += dbl[c] * (h[cp[c]] - h[c]);
     if (dxs) acc_tm += dxs[c];
   }
-  if (p.d_times)
-    for (int i = tid; i <= m; i += CT) acc_tm += p.d_times[(size_t)u * (m + 1) + i] * (i < m ? (double)i / (double)m : 1.0);
+  if (p.d_times) {
+    if (p.grid) {
+      for (int i = tid; i <= m; i += CT) {
+        const double d = i == 0 ? 0.0 : p.d_times[(size_t)u * (m + 1) + i];
+        acc_tm += d;
+        if (p.g_grid) p.g_grid[(size_t)u * (m + 1) + i] = -d;
+      }
+    } else {
+      for (int i = tid; i <= m; i += CT) acc_tm += p.d_times[(size_t)u * (m + 1) + i] * (i < m ? (double)i / (double)m : 1.0);
+    }
+  } else if (p.grid && p.g_grid) {
+    for (int i = tid; i <= m; i += CT) p.g_grid[(size_t)u * (m + 1) + i] = 0.0;
+  }
   const double g_clock = block_sum(acc_clock, red);
   double g_tm = block_sum(acc_tm, red);
 
@@ -471,6 +489,7 @@ static int fill_chain(const vbsky_layout* lay, int32_t U, const int32_t* unit_tr
   p->n = lay->n, p->m = m, p->max_levels = lay->max_levels, p->U = U;
   p->proportions = in->proportions, p->root_proportion = in->root_proportion, p->origin = in->origin;
   p->origin_start = in->origin_start, p->clock_rate = in->clock_rate, p->R = in->R, p->delta = in->delta, p->s = in->s;
+  p->grid = m >= 1 ? in->grid : nullptr;
   return VBSKY_OK;
 }
 
@@ -504,6 +523,7 @@ extern "C" int vbsky_heights_backward(const vbsky_layout* lay, int32_t U, const 
   p.d_bl = d_bl_scaled, p.d_xs = d_xs, p.d_times = d_times, p.d_lam = d_lam, p.d_psi = d_psi, p.d_mu = d_mu;
   p.g_proportions = out->proportions, p.g_root_proportion = out->root_proportion, p.g_origin = out->origin;
   p.g_clock_rate = out->clock_rate, p.g_R = out->R, p.g_delta = out->delta, p.g_s = out->s;
+  p.g_grid = p.grid ? out->grid : nullptr;
   if (p.g_R) VB_CHECK_ARG(m >= 1 && in->R && in->delta && in->s && out->delta && out->s, "skyline gradients need m >= 1 and R, delta, s");
   p.dh = (double*)ws;
   chain_backward_kernel<<<U, CT, 0, (cudaStream_t)stream>>>(p);

@@ -75,7 +75,7 @@ ffi::Error BdskyImpl(cudaStream_t stream, int32_t n, int32_t condition_on_surviv
 // --------------------------------------------------------------------------------------------------- height chain
 vbsky_params Params(F64& proportions, F64& root_proportion, F64& origin, F64& origin_start, F64& clock_rate, F64& R, F64& delta,
                     F64& s, F64& rho) {
-  vbsky_params p;
+  vbsky_params p{};  // grid = NULL: equidistant skyline intervals (the reference's default, bdsky.py:314)
   p.proportions = proportions.typed_data(), p.root_proportion = root_proportion.typed_data();
   p.origin = origin.typed_data(), p.origin_start = origin_start.typed_data(), p.clock_rate = clock_rate.typed_data();
   p.R = R.typed_data(), p.delta = delta.typed_data(), p.s = s.typed_data(), p.rho = rho.typed_data();
@@ -100,7 +100,7 @@ ffi::Error HeightsBackwardImpl(cudaStream_t stream, int64_t layout, S32 unit_tre
   const int32_t U = static_cast<int32_t>(unit_tree.element_count());
   const int32_t m = static_cast<int32_t>(R.dimensions()[1]);
   const vbsky_params in = Params(proportions, root_proportion, origin, origin_start, clock_rate, R, delta, s, rho);
-  vbsky_param_grads out;
+  vbsky_param_grads out{};
   out.proportions = g_proportions->typed_data(), out.root_proportion = g_root_proportion->typed_data();
   out.origin = g_origin->typed_data(), out.clock_rate = g_clock_rate->typed_data();
   out.R = g_R->typed_data(), out.delta = g_delta->typed_data(), out.s = g_s->typed_data(), out.rho = nullptr;
@@ -119,7 +119,7 @@ ffi::Error LoglikImpl(cudaStream_t stream, int64_t layout, int64_t tips, int32_t
   const int32_t m = static_cast<int32_t>(R.dimensions()[1]);
   const vbsky_params in = Params(proportions, root_proportion, origin, origin_start, clock_rate, R, delta, s, rho);
   const vbsky_subst_model model = Model(pi, P, d, Pinv);
-  vbsky_param_grads g;
+  vbsky_param_grads g{};
   g.proportions = g_proportions->typed_data(), g.root_proportion = g_root_proportion->typed_data();
   g.origin = g_origin->typed_data(), g.clock_rate = g_clock_rate->typed_data();
   g.R = g_R->typed_data(), g.delta = g_delta->typed_data(), g.s = g_s->typed_data(), g.rho = g_rho->typed_data();
@@ -134,7 +134,7 @@ ffi::Error ReduceElboImpl(cudaStream_t stream, int32_t T, int32_t n, double scal
                           RF64 out) {
   const int32_t U = static_cast<int32_t>(unit_tree.element_count());
   const int32_t m = static_cast<int32_t>(g_R.dimensions()[1]);
-  vbsky_param_grads g;
+  vbsky_param_grads g{};
   g.proportions = g_proportions.typed_data(), g.root_proportion = g_root_proportion.typed_data();
   g.origin = g_origin.typed_data(), g.clock_rate = g_clock_rate.typed_data();
   g.R = g_R.typed_data(), g.delta = g_delta.typed_data(), g.s = g_s.typed_data(), g.rho = g_rho.typed_data();

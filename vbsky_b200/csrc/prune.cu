@@ -205,6 +205,12 @@ extern "C" int vbsky_prune_spectral_grad(const vbsky_layout* lay, const vbsky_ti
   VB_CHECK_ARG(g && out, "NULL argument");
   return f64::run(lay, tips, U, unit_tree, bl, model, nullptr, ll, out, ws, ws_bytes, stream, g);
 }
+extern "C" int vbsky_prune_param_grad(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, const int32_t* unit_tree,
+                                      const double* bl, const vbsky_subst_model* model, const double* dQ, double* ll,
+                                      double* out, double* dpi, void* ws, size_t ws_bytes, void* stream) {
+  VB_CHECK_ARG(dQ && out, "NULL argument");
+  return f64::run(lay, tips, U, unit_tree, bl, model, nullptr, ll, out, ws, ws_bytes, stream, nullptr, -1, -1, dQ, dpi);
+}
 extern "C" size_t vbsky_prune_workspace_bytes_f32(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, int32_t want_grad) {
   return f32::workspace_bytes(lay, tips, U, want_grad);
 }

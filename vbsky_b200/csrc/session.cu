@@ -33,8 +33,8 @@ extern "C" int vbsky_session_create(const vbsky_layout* lay, const vbsky_tips* t
   s->lay = lay, s->tips = tips, s->U_max = U_max, s->m_max = m_max;
   const size_t n = lay->n, nb = 2 * n - 2, mm = (size_t)std::max(m_max, 1);
   // inputs: max(bl rows, parameter rows); outputs: ll x3 + gradients
-  s->in_doubles = (size_t)U_max * std::max(nb, (n - 2) + 4 + 4 * mm);
-  s->out_doubles = (size_t)U_max * (3 + std::max(nb, (n - 2) + 3 + 4 * mm));
+  s->in_doubles = (size_t)U_max * std::max(nb, (n - 2) + 4 + 4 * mm + (mm + 1));
+  s->out_doubles = (size_t)U_max * (3 + std::max(nb, (n - 2) + 3 + 4 * mm + (mm + 1)));
   s->ws_bytes = std::max(vbsky_prune_workspace_bytes(lay, tips, U_max, 1), vbsky_loglik_workspace_bytes(lay, tips, U_max, m_max));
   if (s->ws_bytes == 0) {
     delete s;
@@ -79,15 +79,15 @@ extern "C" int vbsky_loglik_value_and_grad_host(vbsky_session* s, int32_t U, con
   VB_CHECK_ARG(U >= 1 && U <= s->U_max && m >= 0 && m <= s->m_max, "U=%d, m=%d outside the session's capacity (%d, %d)", U, m, s->U_max, s->m_max);
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t n = s->lay->n, np = n - 2, mm = (size_t)m;
-  // device-side packing: [proportions U*(n-2)] [root_prop U] [origin U] [origin_start U] [clock U] [R|delta|s|rho U*m each]
+  // device-side packing: [proportions U*(n-2)] [root_prop U] [origin U] [origin_start U] [clock U] [R|delta|s|rho U*m each] [grid U*(m+1)]
   double* d = s->d_in;
   vbsky_params din{};
   struct Field { const double* src; const double** dst; size_t cols; };
-  Field f[9] = {{in->proportions, &din.proportions, np}, {in->root_proportion, &din.root_proportion, 1},
-                {in->origin, &din.origin, 1},           {in->origin_start, &din.origin_start, 1},
-                {in->clock_rate, &din.clock_rate, 1},   {in->R, &din.R, mm},
-                {in->delta, &din.delta, mm},            {in->s, &din.s, mm},
-                {in->rho, &din.rho, mm}};
+  Field f[10] = {{in->proportions, &din.proportions, np}, {in->root_proportion, &din.root_proportion, 1},
+                 {in->origin, &din.origin, 1},           {in->origin_start, &din.origin_start, 1},
+                 {in->clock_rate, &din.clock_rate, 1},   {in->R, &din.R, mm},
+                 {in->delta, &din.delta, mm},            {in->s, &din.s, mm},
+                 {in->rho, &din.rho, mm},                {in->grid, &din.grid, mm ? mm + 1 : 0}};
   for (auto& x : f) {
     if (x.src && x.cols) {
       VB_CUDA(cudaMemcpyAsync(d, x.src, (size_t)U * x.cols * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -101,13 +101,14 @@ extern "C" int vbsky_loglik_value_and_grad_host(vbsky_session* s, int32_t U, con
   o += 3 * (size_t)s->U_max;
   vbsky_param_grads dg{};
   struct GField { double* host; double** dev; size_t cols; };
-  GField g[8];
+  GField g[9];
   if (grads) {
-    GField gg[8] = {{grads->proportions, &dg.proportions, np}, {grads->root_proportion, &dg.root_proportion, 1},
+    GField gg[9] = {{grads->proportions, &dg.proportions, np}, {grads->root_proportion, &dg.root_proportion, 1},
                     {grads->origin, &dg.origin, 1},           {grads->clock_rate, &dg.clock_rate, 1},
                     {grads->R, &dg.R, mm},                    {grads->delta, &dg.delta, mm},
-                    {grads->s, &dg.s, mm},                    {grads->rho, &dg.rho, mm}};
-    for (int i = 0; i < 8; ++i) {
+                    {grads->s, &dg.s, mm},                    {grads->rho, &dg.rho, mm},
+                    {in->grid ? grads->grid : nullptr, &dg.grid, mm ? mm + 1 : 0}};
+    for (int i = 0; i < 9; ++i) {
       g[i] = gg[i];
       if (g[i].host && g[i].cols) {
         *g[i].dev = o;
@@ -122,7 +123,7 @@ extern "C" int vbsky_loglik_value_and_grad_host(vbsky_session* s, int32_t U, con
   if (ll_tree) VB_CUDA(cudaMemcpyAsync(ll_tree, d_lt, U * sizeof(double), cudaMemcpyDeviceToHost, stream));
   if (ll_data) VB_CUDA(cudaMemcpyAsync(ll_data, d_ld, U * sizeof(double), cudaMemcpyDeviceToHost, stream));
   if (grads)
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 9; ++i)
       if (g[i].host && g[i].cols)
         VB_CUDA(cudaMemcpyAsync(g[i].host, *g[i].dev, (size_t)U * g[i].cols * sizeof(double), cudaMemcpyDeviceToHost, stream));
   VB_CUDA(cudaStreamSynchronize(stream));

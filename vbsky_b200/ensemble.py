@@ -166,6 +166,34 @@ class Ensemble:
                 _lib.np_ptr(g, C.c_double), _ptr(ll), _ptr(out), _ptr(ws), ws.numel(), C.c_void_p(stream)))
         return ll, out
 
+    def prune_param_grad(self, bl: torch.Tensor, unit_tree: torch.Tensor, dQ, dpi_dtheta=None):
+        """``vbsky_prune_param_grad``: d ll[u] / d theta for an arbitrary direction dQ/dtheta [4, 4] of the rate matrix
+        (need not commute with Q) plus, if the parameter also moves the root frequencies, ``dpi_dtheta`` [4].
+        Returns (ll [U], dll_dtheta [U], per-branch contributions [U, 2n-2], d ll / d pi [U, 4])."""
+        U = bl.shape[0]
+        if bl.dtype != torch.float64 or bl.device != self.device or bl.shape != (U, 2 * self.n - 2):
+            raise ValueError(f"bl must be a float64 [{U}, {2 * self.n - 2}] tensor on {self.device}")
+        if unit_tree.dtype != torch.int32 or unit_tree.device != self.device or unit_tree.shape != (U,):
+            raise ValueError("unit_tree must be an int32 [U] tensor on the ensemble's device")
+        dQ = np.ascontiguousarray(np.asarray(dQ, dtype=np.float64).reshape(16))
+        bl = bl.contiguous()
+        with torch.cuda.device(self.device):
+            need = _lib.lib.vbsky_prune_workspace_bytes(self._layout, self._tips, U, 1)
+            if need == 0:
+                raise _lib.VbskyError(-1, _lib.last_error())
+            ws = self._workspace(need)
+            ll = torch.empty(U, dtype=torch.float64, device=self.device)
+            out = torch.empty(U, 2 * self.n - 2, dtype=torch.float64, device=self.device)
+            dpi = torch.empty(U, 4, dtype=torch.float64, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib.vbsky_prune_param_grad(
+                self._layout, self._tips, U, _ptr(unit_tree), _ptr(bl), C.byref(self._model), _lib.np_ptr(dQ, C.c_double),
+                _ptr(ll), _ptr(out), _ptr(dpi), _ptr(ws), ws.numel(), C.c_void_p(stream)))
+        total = out.sum(1)
+        if dpi_dtheta is not None:
+            total = total + dpi @ torch.as_tensor(np.asarray(dpi_dtheta, dtype=np.float64), device=self.device)
+        return ll, total, out, dpi
+
     def dll_dkappa(self, bl: torch.Tensor, unit_tree: torch.Tensor, kappa: float) -> torch.Tensor:
         """d ll[u] / d kappa for an ensemble built with ``HKY(kappa)`` (one extra evaluation of the pruning kernel)."""
         from .substitution import HKY_dkappa
@@ -206,6 +234,7 @@ class Ensemble:
 
     GRAD_KEYS = ("proportions", "root_proportion", "origin", "clock_rate", "R", "delta", "s", "rho")
     PARAM_KEYS = ("proportions", "root_proportion", "origin", "origin_start", "clock_rate", "R", "delta", "s", "rho")
+    OPTIONAL_KEYS = ("grid",)  # prespecified skyline grid [U, m+1] (bdsky.py:317-319); absent = equidistant intervals
 
     @property
     def tiles(self) -> int:
@@ -224,13 +253,13 @@ class Ensemble:
         and ``vbsky_loglik_backward_complete`` finishes the evaluation."""
         U = unit_tree.shape[0]
         cin = _lib.Params()
-        for k in self.PARAM_KEYS:
+        for k in self.PARAM_KEYS + self.OPTIONAL_KEYS:
             v = params.get(k)
             setattr(cin, k, 0 if v is None or v.numel() == 0 else v.data_ptr())
         cg = None
         if grads is not None:
             cg = _lib.ParamGrads()
-            for k in self.GRAD_KEYS:
+            for k in self.GRAD_KEYS + self.OPTIONAL_KEYS:
                 v = grads.get(k)
                 setattr(cg, k, 0 if v is None or v.numel() == 0 else v.data_ptr())
         out = out if out is not None else {}
@@ -273,12 +302,12 @@ class Ensemble:
         U = unit_tree.shape[0]
         hp = lambda a: 0 if a is None or a.size == 0 else a.ctypes.data
         cin = _lib.Params()
-        for k in self.PARAM_KEYS:
+        for k in self.PARAM_KEYS + self.OPTIONAL_KEYS:
             setattr(cin, k, hp(params.get(k)))
         cg = None
         if grads is not None:
             cg = _lib.ParamGrads()
-            for k in self.GRAD_KEYS:
+            for k in self.GRAD_KEYS + self.OPTIONAL_KEYS:
                 setattr(cg, k, hp(grads.get(k)))
         out = out if out is not None else {}
         for k in ("ll", "tree", "data"):

@@ -56,6 +56,58 @@ def JC69() -> SubstitutionModel:
     return HKY(1.0)
 
 
+_PAIRS = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))  # AC, AG, AT, CG, CT, GT
+
+
+def gtr_rate_matrix(rates, pi) -> np.ndarray:
+    """Q of the general time-reversible model: Q_ij = r_ij pi_j (i != j), rows summing to zero; ``rates`` in the order
+    AC, AG, AT, CG, CT, GT (HKY with base frequencies is rates = (1, kappa, 1, 1, kappa, 1)).  Not normalised."""
+    rates, pi = np.asarray(rates, dtype=np.float64), np.asarray(pi, dtype=np.float64)
+    Q = np.zeros((4, 4))
+    for r, (i, j) in zip(rates, _PAIRS):
+        Q[i, j] = r * pi[j]
+        Q[j, i] = r * pi[i]
+    Q -= np.diag(Q.sum(1))
+    return Q
+
+
+def GTR(rates, pi) -> SubstitutionModel:
+    """Reversible model with arbitrary exchangeabilities and base frequencies as a (pi, P, d, Pinv) model: the rate matrix
+    is similar to the symmetric D^1/2 Q D^-1/2 (D = diag(pi)), whose eigh gives P = D^-1/2 V, Pinv = V^T D^1/2.
+    The reference only constructs uniform-frequency HKY (substitution.py:73-92); the kernels take any such model
+    (dense-matrix path)."""
+    pi = np.asarray(pi, dtype=np.float64)
+    Q = gtr_rate_matrix(rates, pi)
+    sq = np.sqrt(pi)
+    S = (sq[:, None] * Q) / sq[None, :]
+    d, V = np.linalg.eigh((S + S.T) / 2)
+    P, Pinv = V / sq[:, None], V.T * sq[None, :]
+    assert np.allclose(P @ np.diag(d) @ Pinv, Q, atol=1e-12)
+    return SubstitutionModel(pi, P, d, Pinv)
+
+
+def gtr_directions(rates, pi):
+    """The derivative directions of ``gtr_rate_matrix``: a list of (name, dQ/dtheta [4, 4], dpi/dtheta [4]) for the six
+    exchangeabilities and for the three free base-frequency coordinates (pi_i, i = A, C, G, with pi_T = 1 - sum)."""
+    rates, pi = np.asarray(rates, dtype=np.float64), np.asarray(pi, dtype=np.float64)
+    out = []
+    for k, (i, j) in enumerate(_PAIRS):
+        dQ = np.zeros((4, 4))
+        dQ[i, j], dQ[j, i] = pi[j], pi[i]
+        dQ -= np.diag(dQ.sum(1))
+        out.append((f"rate_{'ACGT'[i]}{'ACGT'[j]}", dQ, np.zeros(4)))
+    R = np.zeros((4, 4))
+    for r, (i, j) in zip(rates, _PAIRS):
+        R[i, j] = R[j, i] = r
+    for i in range(3):
+        dpi = np.zeros(4)
+        dpi[i], dpi[3] = 1.0, -1.0
+        dQ = R * dpi[None, :]
+        dQ -= np.diag(dQ.sum(1))
+        out.append((f"pi_{'ACGT'[i]}", dQ, dpi))
+    return out
+
+
 def encode_codes(seqs) -> np.ndarray:
     """n equal-length sequences -> uint8 [L, n] state masks (bit0=A, bit1=C, bit2=G, bit3=T) following
     the BEAST ambiguity table of substitution.py:10-35.  Unknown characters raise KeyError."""
