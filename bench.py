@@ -351,6 +351,35 @@ class Evaluator:
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         return tms.item() / steps, kms / max(klaunches, 1), clocks
 
+    def time_graph_replay(self, steps):
+        """The same step captured once into a CUDA graph and replayed (single rank only): what a fitting loop does with a
+        launch-bound step.  Returns ms per step, or None if capture is unavailable."""
+        torch = self.torch
+        if self.world > 1:
+            return None
+        try:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.step()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps
+        except Exception:
+            return None
+
     def close(self):
         self.ens.close()
 
@@ -516,7 +545,8 @@ def main():
                 o = Evaluator(name, 0, dev, 0, 1)
                 oms, okern, _ = o.time_steps(10, 3)
                 ost = o.ens.last_stats()
-                others[name] = {"ms_per_step": oms, "evals_per_s": 1e3 / oms, "units": o.T * o.K,
+                gms = o.time_graph_replay(20)
+                others[name] = {"ms_per_step": oms, "evals_per_s": 1e3 / oms, "ms_per_step_graph_replay": gms, "units": o.T * o.K,
                                 "shape": f"{o.T} trees x {o.n} tips x {o.S} patterns, K={o.K}, m={o.m}",
                                 "prune_kernel_ms": okern, "roofline_frac": ost["algorithmic_bytes"] / (okern * 1e-3) / 1e9 / peak if okern > 0 else None}
                 o.close()
