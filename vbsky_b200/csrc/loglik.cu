@@ -48,6 +48,30 @@ static int loglik_plan(const vbsky_layout* lay, const vbsky_tips* tips, int U, i
   return VBSKY_OK;
 }
 
+// The tree prior (bdsky_kernel: one CTA per unit, a serial m-step recursion -- latency-bound, ~0.1-0.2 ms whatever U is)
+// does not depend on the data term, so it runs on a side stream next to tables_kernel / prune_kernel: fork after the
+// height chain, join before the call returns its stream to the caller.  One side stream + two events per (host thread,
+// device), created on first use; event record / wait are capturable, so CUDA-graph capture of the fused call still works.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int side_stream(int device, SideStream** out) {
+  static thread_local std::vector<std::pair<int, SideStream>> pool;
+  for (auto& e : pool)
+    if (e.first == device) {
+      *out = &e.second;
+      return VBSKY_OK;
+    }
+  SideStream ss;
+  VB_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+  VB_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+  pool.push_back({device, ss});
+  *out = &pool.back().second;
+  return VBSKY_OK;
+}
+
 }  // namespace vbsky
 
 using namespace vbsky;
@@ -88,6 +112,7 @@ extern "C" int vbsky_loglik_forward_partial(const vbsky_layout* lay, const vbsky
   if (rc != VBSKY_OK) return rc;
   if (want_grad) VB_CHECK_ARG(grads != nullptr, "grads is NULL");
   const bool tree = flags & VBSKY_TERM_TREE, data = flags & VBSKY_TERM_DATA;
+  if (data && (flags & VBSKY_PRUNE_F32)) VB_CHECK_ARG(tile_begin == 0 && tile_end == tips->tiles, "the fp32 data term does not take a tile sub-range");
   LoglikPlan pl;
   rc = loglik_plan(lay, tips, U, m, &pl);
   if (rc != VBSKY_OK) return rc;
@@ -99,25 +124,38 @@ extern "C" int vbsky_loglik_forward_partial(const vbsky_layout* lay, const vbsky
   rc = vbsky_heights_forward(lay, U, unit_tree, tree ? m : 0, in, D(pl.heights), D(pl.bl), tree ? D(pl.xs) : nullptr,
                              tree ? D(pl.times) : nullptr, D(pl.lam), D(pl.psi), D(pl.mu), stream);
   if (rc != VBSKY_OK) return rc;
+  SideStream* side = nullptr;
+  if (tree && data && getenv("VBSKY_NO_SIDE_STREAM") == nullptr) {
+    rc = side_stream(lay->device, &side);
+    if (rc != VBSKY_OK) return rc;
+    VB_CUDA(cudaEventRecord(side->fork, st));
+    VB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
   if (tree) {
     rc = vbsky_bdsky_value_and_grad(U, n, m, D(pl.lam), D(pl.psi), D(pl.mu), in->rho, D(pl.xs), D(pl.times),
                                     (flags & VBSKY_CONDITION_ON_SURVIVAL) ? 1 : 0, D(pl.lt), want_grad ? D(pl.dlam) : nullptr,
                                     D(pl.dpsi), D(pl.dmu), want_grad ? grads->rho : nullptr, D(pl.dxs), D(pl.dtimes),
-                                    b + pl.bdsky, pl.bdsky_bytes, stream);
-    if (rc != VBSKY_OK) return rc;
+                                    b + pl.bdsky, pl.bdsky_bytes, side ? (void*)side->stream : stream);
+    if (side) {  // join is enqueued after the data term below; record it now so that an early return cannot leave a dangling fork
+      cudaError_t e = cudaEventRecord(side->join, side->stream);
+      if (rc == VBSKY_OK && e != cudaSuccess) rc = set_error(VBSKY_ECUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != VBSKY_OK) {
+      if (side) cudaStreamWaitEvent(st, side->join, 0);
+      return rc;
+    }
   } else if (want_grad && grads->rho && m >= 1) {
     VB_CUDA(cudaMemsetAsync(grads->rho, 0, (size_t)U * m * sizeof(double), st));
   }
   if (data) {
-    if (flags & VBSKY_PRUNE_F32) VB_CHECK_ARG(tile_begin == 0 && tile_end == tips->tiles, "the fp32 data term does not take a tile sub-range");
     rc = (flags & VBSKY_PRUNE_F32)
              ? vbsky_prune_value_and_grad_f32(lay, tips, U, unit_tree, D(pl.bl), model, nullptr, D(pl.ld),
                                               want_grad ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream)
              : vbsky_prune_value_and_grad_tiles(lay, tips, U, unit_tree, D(pl.bl), model, tile_begin, tile_end, nullptr, D(pl.ld),
                                                 want_grad ? D(pl.dbl) : nullptr, b + pl.prune, pl.prune_bytes, stream);
-    if (rc != VBSKY_OK) return rc;
   }
-  return VBSKY_OK;
+  if (side) VB_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // the caller's stream owns every result from here on
+  return rc;
 }
 
 extern "C" double* vbsky_loglik_exchange_buffer(const vbsky_layout* lay, const vbsky_tips* tips, int32_t U, int32_t m, void* ws,

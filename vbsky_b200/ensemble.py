@@ -60,6 +60,7 @@ class Ensemble:
         info = (C.c_int32 * 8)()
         _lib.check(_lib.lib.vbsky_layout_info(self._layout, info))
         self.depth_up, self.depth_down, self.max_levels = info[2], info[3], info[4]
+        self.mean_stored_messages = info[6]  # per tree: non-root internal nodes that are not cherries (their messages travel through HBM)
 
     def close(self):
         if getattr(self, "_session", None):
