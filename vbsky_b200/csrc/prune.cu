@@ -53,6 +53,15 @@ constexpr int CODE_ROW = TILE;        // bytes of tip codes per (step, child)
 constexpr int GCH = 8;                // branch gradients staged per reduction round
 constexpr int GROW = 33;              // per-warp staging row: one value per lane (its two sites pre-added) + pad
 constexpr int OFF_STAGE = 128;
+#ifdef VBSKY_GRAD_SHUFFLE
+constexpr bool GRAD_SHUFFLE = true;   // branch gradients reduced with warp shuffles (no shared-memory staging block)
+#else
+constexpr bool GRAD_SHUFFLE = false;
+#endif
+#ifndef VBSKY_MIN_CTAS
+#define VBSKY_MIN_CTAS 3
+#endif
+constexpr int MIN_CTAS = VBSKY_MIN_CTAS;  // resident CTAs per SM the register allocation is sized for
 
 __device__ __constant__ uint8_t kRankToMask[16] = {1, 2, 4, 8, 15, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 0};
 
