@@ -222,7 +222,7 @@ def _t1(p):
     return p["transform"]["t1"]
 
 
-def config1(names, seqs, n_trees=3, n_tips=10, n_iter=2, seed=0):
+def config1(names, seqs, n_trees=10, n_tips=10, n_iter=2, seed=0):
     rng = np.random.default_rng(seed)
     tds, otds, tip_r, tip_o, rows_all, newicks = [], [], [], [], [], []
     for t in range(n_trees):

@@ -58,6 +58,11 @@ constexpr bool GRAD_SHUFFLE = true;   // branch gradients reduced with warp shuf
 #else
 constexpr bool GRAD_SHUFFLE = false;
 #endif
+#ifdef VBSKY_TIPQ_COMPUTE
+constexpr bool TIPQ_COMPUTE = true;   // down pass: G m of a tip child computed instead of gathered from its Q table
+#else
+constexpr bool TIPQ_COMPUTE = false;
+#endif
 #ifndef VBSKY_MIN_CTAS
 #define VBSKY_MIN_CTAS 3
 #endif

@@ -100,6 +100,10 @@ class Ensemble:
             _lib.check(_lib.lib.vbsky_tips_set_counts(self._tips, _lib.np_ptr(counts, C.c_double)))
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
+        """One cached scratch buffer per Ensemble, grown on demand.  It is shared by every call made through this object,
+        so all of them must be issued on ONE stream (or be ordered by the caller): two streams evaluating through the same
+        Ensemble concurrently would overwrite each other's step tables.  Use one Ensemble per stream / host thread (the
+        handles underneath are immutable and may be shared; tests/test_multidevice_gpu.py does exactly that)."""
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
