@@ -80,8 +80,14 @@ def test_sequential_fit_reproduces_reference_loop(cuda):
     model.set_params(lp["init_global"], lp["init_local"])
     hist = model.fit(n_iter=lp["n_iter"], step_size=lp["step_size"], sequential=True,
                      eps_fn=lambda i, j: _eps(lp["eps"][i][j], g["n_tips"], cuda))
-    want = np.array(lp["fs"]).T  # fs[j][i] -> [i][j]
-    np.testing.assert_allclose(np.array(hist), want, rtol=1e-9)
+    want = np.array(lp["fs"]).T.reshape(-1)  # fs[j][i] -> visits in iteration-major order
+    got = np.array(hist).reshape(-1)
+    # the visits the reference itself reproduces to 1e-9 under a 1e-13 perturbation of its draws (loop.stable_visits): beyond
+    # them the trajectory sits on a discontinuity of the reference's objective (bdsky.py:62-79) and nothing is comparable
+    nv = lp["stable_visits"]
+    assert nv >= g["n_trees"] + 3
+    np.testing.assert_allclose(got[:nv], want[:nv], rtol=1e-9)
+    assert np.isfinite(got).all()
     ens.close()
 
 

@@ -40,7 +40,10 @@ def test_oracle_step_matches_reference_fixture():
 
 def test_oracle_loop_matches_reference_fixture():
     """Two iterations of SeqData.loop (fasta.py:456-487) restated with the oracle's step + Adagrad rule, replaying the
-    recorded base draws: the per-visit losses ``fs`` of the reference's own loop."""
+    recorded base draws: the per-visit losses ``fs`` of the reference's own loop.  Compared over the visits the
+    reference itself reproduces to 1e-9 when its draws are perturbed by 1e-13 (``loop.stable_visits``, measured by
+    tests/golden/make_golden.py): beyond them the trajectory sits on a discontinuity of the reference's objective (the
+    extinction fallback of bdsky.py:62-79) that Adagrad's normalised steps amplify, and no two implementations agree."""
     g, tds, tips, flows = _setup()
     Q = osub.HKY(g["kappa"])
     lp = g["loop"]
@@ -49,8 +52,11 @@ def test_oracle_loop_matches_reference_fixture():
     leaves = lambda tree: [(k, kk) for k in tree for kk in ("mu", "log_sigma")]
     st_g = {kl: oopt.adagrad_init(glob[kl[0]][kl[1]]) for kl in leaves(glob)}
     st_l = [{kl: oopt.adagrad_init(l[kl[0]][kl[1]]) for kl in leaves(l)} for l in loc]
+    assert lp["stable_visits"] >= g["n_trees"] + 3  # at least one full pass over the trees and into the second
     for i in range(lp["n_iter"]):
         for j in range(g["n_trees"]):
+            if i * g["n_trees"] + j >= lp["stable_visits"]:
+                return
             cur_g = {k: {kk: st_g[(k, kk)][0] for kk in ("mu", "log_sigma")} for k in glob}
             cur_l = {k: {kk: st_l[j][(k, kk)][0] for kk in ("mu", "log_sigma")} for k in loc[j]}
             f, grads = oopt.step_value_and_grad(_params(cur_g, cur_l), flows, tds[j], tips[j], lp["eps"][i][j], Q,
