@@ -225,6 +225,55 @@ def test_prune_large_trees_vs_c_port(cuda, n, S, caterpillar):
     ens.close()
 
 
+@pytest.mark.parametrize("levels,S", [(7, 300), (9, 520)])
+def test_prune_perfectly_balanced_tree_uses_the_deep_stack(cuda, levels, S):
+    """A perfect binary tree needs log2(n) + 1 parked vectors (8 at 128 tips, 10 at 512): more than the five stack slots
+    kept in shared memory, so the deepest slots live in the CTA's global deep stack (three CTAs per SM stay resident).
+    Value, per-site values and the full gradient against the C port."""
+    import oracle.cref as cref
+    from vbsky_b200.ensemble import Ensemble
+    from vbsky_b200.substitution import HKY
+    from vbsky_b200.synth import evolve_codes, sample_heights
+    from vbsky_b200.tips import PackedTips
+    from vbsky_b200.tree_data import TreeData
+
+    n = 2 ** levels
+    edges, nxt = [], 1
+    frontier = [("i", 0)]
+    for lev in range(levels):
+        new = []
+        for u in frontier:
+            for _ in range(2):
+                v = ("t", nxt) if lev == levels - 1 else ("i", nxt)
+                nxt += 1
+                edges.append((u, v))
+                new.append(v)
+        frontier = new
+    td, _ = TreeData.from_edges(edges)
+    assert td.n == n
+    rng = np.random.default_rng(levels)
+    st = rng.uniform(0.0, 1.0, n)
+    st[0] = 0.0
+    td = TreeData(td.postorder, td.child_parent, td.parent_child, st)
+    Q, oQ = HKY(2.7), osub.HKY(2.7)
+    sh = sample_heights(td, 2, rng, origin=1.0)
+    bl = sh.branch_lengths * 0.03
+    codes = evolve_codes(td, bl[0], oQ, S, rng, missing=0.02)
+    counts = rng.integers(1, 3, S).astype(np.float64)
+    ut = torch.zeros(2, dtype=torch.int32, device=cuda)
+    ens = Ensemble([td], [PackedTips(codes, counts)], Q, device=cuda)
+    assert max(ens.depth_up, ens.depth_down) > 5
+    ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), ut, want_grad=True, want_site_ll=True)
+    smem_deep = ens.last_stats()["smem"]
+    for u in range(2):
+        tot, g, sll = cref.prune(_oracle_td(td), bl[u], oQ, codes, counts, True, True)
+        np.testing.assert_allclose(site[u].cpu().numpy(), sll, rtol=LL_RTOL, atol=1e-11)
+        np.testing.assert_allclose(ll[u].item(), tot, rtol=LL_RTOL)
+        np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    ens.close()
+    assert smem_deep <= 76800  # three CTAs per SM
+
+
 def test_prune_many_units_single_pattern(cuda):
     """Ragged extremes: one site pattern (S=1, a single partly-filled tile) and thousands of units."""
     from vbsky_b200.ensemble import Ensemble
