@@ -90,3 +90,22 @@ def test_two_rank_allreduce_matches_single_process():
     # the local block really needs the exchange: with K = 3 units per tree dealt over 2 ranks, neither rank alone has it
     alone = pack_reference(*_local(shard_units(T, K, 0, 2)), T, N_TIPS, M, K).numpy()
     assert not np.allclose(alone[3 + 4 * M:], want[3 + 4 * M:])
+
+
+def test_shard_plan_and_tile_ranges():
+    """Units are preferred (no in-step exchange) while every rank keeps enough of them; otherwise site-pattern blocks.
+    Tile ranges are a contiguous, balanced partition."""
+    from vbsky_b200.parallel import shard_plan, tile_range
+
+    assert shard_plan(1000, 117, 1) == (1, 1)
+    assert shard_plan(1000, 117, 8) == (8, 1)      # config 3: 125 units per rank
+    assert shard_plan(16, 40, 8) == (1, 8)         # config 2: one tree, 16 samples -> 5 tiles per rank
+    assert shard_plan(16, 4, 8) == (8, 1)          # fewer tiles than ranks: nothing to split
+    assert shard_plan(10000, 8, 8) == (8, 1)       # config 4
+    for tiles in (1, 5, 40, 117, 391):
+        for parts in (1, 2, 3, 8):
+            rs = [tile_range(tiles, p, parts) for p in range(parts)]
+            assert rs[0][0] == 0 and rs[-1][1] == tiles
+            assert all(a[1] == b[0] for a, b in zip(rs[:-1], rs[1:]))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
