@@ -114,6 +114,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def native_so_loaded():
+    """In-tree shared objects mapped into this process (from /proc/self/maps): evidence of which native code ran."""
+    out = set()
+    try:
+        for line in open("/proc/self/maps"):
+            path = line.split(None, 5)[-1].strip() if line.count(" ") >= 5 else ""
+            if path.startswith(ROOT) and ".so" in path:
+                out.add(os.path.relpath(path, ROOT))
+    except OSError:
+        pass
+    return sorted(out)
+
+
 def global_draws(K, m):
     """One draw of the global skyline parameters per MC sample (shared by both arms)."""
     return np.random.default_rng(PARAM_SEED).lognormal(0.0, 0.5, (K, m))
@@ -238,8 +251,9 @@ def run_reference(args):
                                    f"BDSKY prior, gradients); both pinned to the reference's source (tests/test_reference_pin.py). The JAX "
                                    f"reference itself is not installable offline (no jax/msprime/tskit wheels)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "native_note": "only oracle/libvbsky_oracle.so is loaded by this arm; vbsky_b200 is not imported",
+        "native_so_loaded": native_so_loaded(),  # only oracle/libvbsky_oracle.so: vbsky_b200 is never imported by this arm
     }
+    assert "vbsky_b200" not in sys.modules and not any("libvbsky_b200" in p for p in line["native_so_loaded"])
     print(json.dumps(line), flush=True)
 
 
@@ -526,6 +540,7 @@ def main():
                         if ev.tile_range is None else
                         "site-block mode: pinned host parameters -> device, the sharded step with its in-step all-reduce, reduced payload -> pinned host"},
         "gpu_launches": int(ev.launches_per_step * args.steps),
+        "native_so_loaded": native_so_loaded(),
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "kernel": "prune_kernel<grad, clip-free>", "achieved": achieved, "peak": peak, "unit": "GB/s",

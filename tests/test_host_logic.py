@@ -330,3 +330,22 @@ def test_merges_to_tree_numbering_matches_newick_route():
     assert all(td.sample_times[nm[s]] == float(i) for i, s in enumerate(names))
     td2, map2 = TreeData.from_newick(merges_to_newick(merges, heights, names))
     assert np.array_equal(td2.child_parent, td.child_parent) and all(map2[s] == nm[s] for s in names)
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """bench.py --impl reference (the CPU arm) must run without importing vbsky_b200: its JSON line lists the in-tree shared
+    objects mapped into the process, and only the oracle's C port may be there."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
+                          "--warmup", "1", "--ref-units-per-step", "2"], capture_output=True, text=True, timeout=600,
+                         env={**os.environ, "OMP_NUM_THREADS": "1"})  # as under torchrun: the arm must set its own thread count
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["native_so_loaded"] == ["oracle/libvbsky_oracle.so"]
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)  # not the launcher's OMP_NUM_THREADS=1
+    assert line["config"]["workload"].startswith("tiny:") and line["e2e"]["h2d_bytes_per_step"] == 0
