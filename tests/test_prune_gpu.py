@@ -225,11 +225,12 @@ def test_prune_large_trees_vs_c_port(cuda, n, S, caterpillar):
     ens.close()
 
 
-@pytest.mark.parametrize("levels,S", [(7, 300), (9, 520)])
-def test_prune_perfectly_balanced_tree_uses_the_deep_stack(cuda, levels, S):
+@pytest.mark.parametrize("levels,S,units", [(7, 300, 2), (7, 300, 900), (9, 520, 600)])
+def test_prune_perfectly_balanced_tree_and_the_deep_stack(cuda, levels, S, units):
     """A perfect binary tree needs log2(n) + 1 parked vectors (8 at 128 tips, 10 at 512): more than the five stack slots
-    kept in shared memory, so the deepest slots live in the CTA's global deep stack (three CTAs per SM stay resident).
-    Value, per-site values and the full gradient against the C port."""
+    that fit beside three resident CTAs.  With a couple of waves of work items everything stays in shared memory (fewer
+    resident CTAs, fastest walk); with many waves (>= 1776 items) the deepest slots move to the CTA's global deep stack
+    and three CTAs per SM stay resident.  Both modes: value, per-site values and the full gradient against the C port."""
     import oracle.cref as cref
     from vbsky_b200.ensemble import Ensemble
     from vbsky_b200.substitution import HKY
@@ -256,22 +257,26 @@ def test_prune_perfectly_balanced_tree_uses_the_deep_stack(cuda, levels, S):
     st[0] = 0.0
     td = TreeData(td.postorder, td.child_parent, td.parent_child, st)
     Q, oQ = HKY(2.7), osub.HKY(2.7)
-    sh = sample_heights(td, 2, rng, origin=1.0)
-    bl = sh.branch_lengths * 0.03
-    codes = evolve_codes(td, bl[0], oQ, S, rng, missing=0.02)
+    sh = sample_heights(td, 3, rng, origin=1.0)
+    bl3 = sh.branch_lengths * 0.03
+    bl = bl3[np.arange(units) % 3]  # three distinct samples of heights, repeated
+    codes = evolve_codes(td, bl3[0], oQ, S, rng, missing=0.02)
     counts = rng.integers(1, 3, S).astype(np.float64)
-    ut = torch.zeros(2, dtype=torch.int32, device=cuda)
+    ut = torch.zeros(units, dtype=torch.int32, device=cuda)
     ens = Ensemble([td], [PackedTips(codes, counts)], Q, device=cuda)
     assert max(ens.depth_up, ens.depth_down) > 5
     ll, dll, site = ens.prune(torch.as_tensor(bl, device=cuda), ut, want_grad=True, want_site_ll=True)
-    smem_deep = ens.last_stats()["smem"]
-    for u in range(2):
+    smem = ens.last_stats()["smem"]
+    deep_mode = units * ens.tiles >= 4 * 148 * 3
+    assert (smem <= 76800) == deep_mode  # three CTAs per SM only in the throughput regime
+    for u in range(min(units, 3)):
         tot, g, sll = cref.prune(_oracle_td(td), bl[u], oQ, codes, counts, True, True)
         np.testing.assert_allclose(site[u].cpu().numpy(), sll, rtol=LL_RTOL, atol=1e-11)
         np.testing.assert_allclose(ll[u].item(), tot, rtol=LL_RTOL)
         np.testing.assert_allclose(dll[u].cpu().numpy(), g, rtol=GRAD_RTOL, atol=GRAD_RTOL * np.abs(g).max())
+    for u in range(3, units):  # identical inputs give bitwise identical outputs whichever CTA drew the item
+        assert torch.equal(ll[u], ll[u % 3]) and torch.equal(dll[u], dll[u % 3])
     ens.close()
-    assert smem_deep <= 76800  # three CTAs per SM
 
 
 def test_prune_many_units_single_pattern(cuda):

@@ -72,6 +72,7 @@ struct vbsky_layout {
   std::vector<int32_t> h_dchunk_start;        // [T][chunk_cap+1] first step of each (variable-length, <= kChunkSteps) down chunk
   std::vector<int32_t> h_n_dchunks;           // [T] number of down chunks
   std::vector<int32_t> h_n_msgs;              // [T] messages that travel through scratch (non-root internal nodes minus cherries)
+  std::vector<vbsky::Op> h_chunk_meta;        // [T][chunk_cap] {first step, steps, first message, end message} per down chunk
   int32_t chunk_cap = 0;
   std::vector<int32_t> h_child_parent;        // [T][N]
   std::vector<int32_t> h_parent_child;        // [T][N][2]
@@ -89,6 +90,8 @@ struct vbsky_layout {
   int32_t* d_msg_start = nullptr;
   int32_t* d_dchunk_start = nullptr;
   int32_t* d_n_dchunks = nullptr;
+  int32_t* d_n_msgs = nullptr;
+  vbsky::Op* d_chunk_meta = nullptr;
   int32_t* d_child_parent = nullptr;
   int32_t* d_parent_child = nullptr;
   double* d_lst = nullptr;

@@ -46,7 +46,8 @@ struct SlotPool {
 
 // Build both schedules of one tree.  pc = parent_child [N][2].
 int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, int32_t* msg_rows,
-               int32_t* msg_start, int32_t* dchunk_start, int32_t* n_dchunks, int32_t* n_msgs, int* depth_up, int* depth_down) {
+               int32_t* msg_start, int32_t* dchunk_start, int32_t* n_dchunks, int32_t* n_msgs, Op* chunk_meta, int* depth_up,
+               int* depth_down) {
   const int N = 2 * n - 1, root = N - 1;
   auto internal = [n](int v) { return v >= n; };
   // A "cherry" is a non-root internal node whose two children are tips.  Its message is cheap to recompute from the two
@@ -234,6 +235,9 @@ int build_tree(int n, const int32_t* pc, Op* up, Op* down, int32_t* down_nodes, 
     }
     dchunk_start[nchunk] = n - 1, msg_start[nchunk] = nmsg;
     *n_dchunks = nchunk, *n_msgs = nmsg;
+    // one 16-byte record per chunk for the producer lane: {first step, steps, first message, end message}
+    for (int c = 0; c < nchunk; ++c)
+      chunk_meta[c] = Op{dchunk_start[c], dchunk_start[c + 1] - dchunk_start[c], msg_start[c], msg_start[c + 1]};
     *depth_down = std::max(pool.high, 1);
   }
   return VBSKY_OK;
@@ -269,6 +273,8 @@ extern "C" void vbsky_layout_destroy(vbsky_layout* lay) {
   cudaFree(lay->d_msg_start);
   cudaFree(lay->d_dchunk_start);
   cudaFree(lay->d_n_dchunks);
+  cudaFree(lay->d_n_msgs);
+  cudaFree(lay->d_chunk_meta);
   cudaFree(lay->d_child_parent);
   cudaFree(lay->d_parent_child);
   cudaFree(lay->d_lst);
@@ -301,6 +307,7 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   lay->h_dchunk_start.assign((size_t)T * (chunk_cap + 1), 0);
   lay->h_n_dchunks.assign(T, 0);
   lay->h_n_msgs.assign(T, 0);
+  lay->h_chunk_meta.assign((size_t)T * std::max(chunk_cap, 1), Op{0, 0, 0, 0});
   lay->h_child_parent.assign(child_parent, child_parent + (size_t)T * N);
   lay->h_parent_child.assign(parent_child, parent_child + (size_t)T * N * 2);
   lay->h_siblings.assign((size_t)T * N, -1);
@@ -339,7 +346,7 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
     rc = build_tree(n, pc, &lay->h_up[(size_t)t * (n - 1)], &lay->h_down[(size_t)t * (n - 1)],
                     &lay->h_down_nodes[(size_t)t * (2 * n - 2)], &lay->h_msg_rows[(size_t)t * std::max(n - 2, 1)],
                     &lay->h_msg_start[(size_t)t * (chunk_cap + 1)], &lay->h_dchunk_start[(size_t)t * (chunk_cap + 1)],
-                    &lay->h_n_dchunks[t], &lay->h_n_msgs[t], &du, &dd);
+                    &lay->h_n_dchunks[t], &lay->h_n_msgs[t], &lay->h_chunk_meta[(size_t)t * std::max(chunk_cap, 1)], &du, &dd);
     if (rc != VBSKY_OK) break;
     lay->depth_up = std::max(lay->depth_up, du);
     lay->depth_down = std::max(lay->depth_down, dd);
@@ -406,6 +413,8 @@ extern "C" int vbsky_layout_create(int32_t T, int32_t n, const int32_t* parent_c
   VB_UP(d_msg_start, h_msg_start)
   VB_UP(d_dchunk_start, h_dchunk_start)
   VB_UP(d_n_dchunks, h_n_dchunks)
+  VB_UP(d_n_msgs, h_n_msgs)
+  VB_UP(d_chunk_meta, h_chunk_meta)
   VB_UP(d_child_parent, h_child_parent)
   VB_UP(d_parent_child, h_parent_child)
   VB_UP(d_lst, h_lst)

@@ -63,6 +63,10 @@ constexpr bool TIPQ_COMPUTE = true;   // down pass: G m of a tip child computed 
 #else
 constexpr bool TIPQ_COMPUTE = false;
 #endif
+#ifndef VBSKY_MSG_PREFETCH
+#define VBSKY_MSG_PREFETCH 0
+#endif
+constexpr int MSG_PREFETCH = VBSKY_MSG_PREFETCH;  // messages prefetched into L2 ahead of the ring (0 = off)
 #ifndef VBSKY_MIN_CTAS
 #define VBSKY_MIN_CTAS 3
 #endif
@@ -103,6 +107,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// Pull a range of global memory into L2 ahead of its use (no destination, no completion to wait for).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 struct RingState {
