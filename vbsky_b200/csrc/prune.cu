@@ -63,6 +63,16 @@ constexpr bool TIPQ_COMPUTE = true;   // down pass: G m of a tip child computed 
 #else
 constexpr bool TIPQ_COMPUTE = false;
 #endif
+#ifdef VBSKY_NO_HOIST_CODES
+constexpr bool HOIST_CODES = false;
+#else
+constexpr bool HOIST_CODES = true;   // tip codes of a step are loaded together with its op word
+#endif
+#ifdef VBSKY_SHALLOW_MATVEC
+constexpr bool SHALLOW_MATVEC = true;  // structured 4x4 product with one dependency level less and four more additions
+#else
+constexpr bool SHALLOW_MATVEC = false;
+#endif
 #ifndef VBSKY_MSG_PREFETCH
 #define VBSKY_MSG_PREFETCH 0
 #endif
