@@ -47,7 +47,10 @@ constexpr int CT = TILE / NS;         // consumer threads
 constexpr int NCW = CT / 32;          // consumer warps
 constexpr int THREADS = CT + 32;      // + producer warp
 constexpr int CH = kChunkSteps;       // steps per ring stage
-constexpr int NST = 2;                // step-chunk ring stages
+#ifndef VBSKY_NST
+#define VBSKY_NST 3
+#endif
+constexpr int NST = VBSKY_NST;        // step-chunk ring stages
 constexpr int NMS_MAX = 4;            // message ring slots available; prune_config uses the third when it costs no resident CTA
 constexpr int CODE_ROW = TILE;        // bytes of tip codes per (step, child)
 constexpr int GCH = 8;                // branch gradients staged per reduction round
