@@ -71,6 +71,11 @@ constexpr bool HOIST_CODES = false;
 #else
 constexpr bool HOIST_CODES = true;   // tip codes of a step are loaded together with its op word
 #endif
+#ifdef VBSKY_OP_PREFETCH
+constexpr bool OP_PREFETCH = true;   // the next step's op word is loaded one step ahead
+#else
+constexpr bool OP_PREFETCH = false;
+#endif
 #ifdef VBSKY_SHALLOW_MATVEC
 constexpr bool SHALLOW_MATVEC = true;  // structured 4x4 product with one dependency level less and four more additions
 #else
